@@ -1,0 +1,172 @@
+/*
+ * pastar_gpu.h — C ABI of the B200-native PA-Star data-parallel core.
+ *
+ * The reference (Gabrielcarvfer/mpi_pastar_msa) has no FFI seam: its hot path
+ * is reached through C++ template classes and three singletons.  This header
+ * is the boundary a maintainer binds instead; every entry point names the
+ * reference interface it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the reference-side shim for each.
+ *
+ * Conventions
+ *   - every call returns a pg_status (0 = ok); no exception crosses the ABI;
+ *     pg_last_error(ctx) gives the message of the last failure.
+ *   - plain pointers and sizes only.  Entry points ending in _dev take DEVICE
+ *     pointers (and a cudaStream_t passed as void*); all others take HOST
+ *     pointers and do their own host<->device copies.
+ *   - there is no CPU fallback: without a CUDA device pg_ctx_create fails
+ *     with PG_ERR_CUDA.
+ *   - a context is bound to one device and is not thread-safe; use one
+ *     context per host thread / per GPU.
+ *
+ * Record layouts (binary compatible with the reference)
+ *   pg_node  = Node<N>   : uint16 pos[N]; pad to 4; int32 f; int32 g; int32 parenti
+ *              (pastar/include/Node.h:28-49, Coord.h:68; sizes in SURVEY F7)
+ *   pg_succ  = pg_node + uint32 owner            (owner = Coord<N>::get_id(vec_size))
+ *   Strides: pg_node_stride(N) = ((2N+3)&~3)+12, pg_succ_stride(N) = that + 4.
+ */
+#ifndef PASTAR_GPU_H
+#define PASTAR_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_MAX_SEQ 16
+#define PG_ABI_VERSION 1
+
+typedef enum {
+    PG_OK = 0,
+    PG_ERR_ARG = 1,         /* bad argument (null, N unsupported, ...)                         */
+    PG_ERR_CUDA = 2,        /* CUDA runtime failure, or no device                              */
+    PG_ERR_UNSUPPORTED = 3, /* problem outside the supported domain (packed key > 128 bits)    */
+    PG_ERR_CAPACITY = 4,    /* closed/open table or open-list pool exhausted                   */
+    PG_ERR_STATE = 5,       /* call out of order (e.g. expand before pg_build_pair_tables)     */
+    PG_ERR_HASH_SHIFT = 6   /* hash shift outside 0..21: CoordHash.cpp:240-242 throws here     */
+} pg_status;
+
+/* hashType, pastar/include/Coord.h:28 (same numeric values) */
+typedef enum { PG_HASH_FZORDER = 0, PG_HASH_PZORDER = 1, PG_HASH_FSUM = 2, PG_HASH_PSUM = 3 } pg_hash_type;
+
+typedef struct pg_ctx pg_ctx;
+
+static inline int pg_node_stride(int n) { return ((2 * n + 3) & ~3) + 12; }
+static inline int pg_succ_stride(int n) { return ((2 * n + 3) & ~3) + 16; }
+
+/* ------------------------------------------------------------------ host-side producers */
+
+/* Replaces Cost::Cost / Cost::cost (pastar/Cost.cpp:12-271, include/Cost.h:13,49):
+ * writes the 90x90 PAM250-as-cost table (raw-ASCII indexed, unset pairs 0). */
+void pg_default_cost_table(int32_t out90x90[90 * 90]);
+
+/* Replaces weightAltschulsRationale2 (pastar/WeightedSP.cpp:424-519): float pair
+ * weights, n x n row-major, float-operation-for-float-operation equal to the
+ * reference.  Host code (serial, float-order sensitive; the reference keeps it
+ * on the host too).  Unlike the reference (fixed 1000x1000 scratch, heap
+ * overflow at L >= 999) any length is accepted. */
+int pg_host_weights(int n_seq, const char *const *seqs, const int *lens, float *w_out);
+
+/* ------------------------------------------------------------------ context */
+
+/* Replaces Sequences::set_seq + the Cost/HeuristicHPair singletons' state
+ * (pastar/Sequences.cpp:39-51, include/Sequences.h:19-28).  Uploads residues,
+ * cost table (NULL = pg_default_cost_table), gap constants (Cost.h:13: 30/30/30)
+ * and the truncated pair weights (int)weightMatrix[i][j] (n x n, NULL = all 1).
+ * device < 0 keeps the current CUDA device. */
+int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens, const int32_t *cost90x90, int gap_open,
+                  int gap_ext, int gap_gap, const int32_t *w_int, int device, pg_ctx **out);
+void pg_ctx_destroy(pg_ctx *ctx);
+const char *pg_last_error(const pg_ctx *ctx);
+int pg_abi_version(void);
+
+/* ------------------------------------------------------------------ (1) pairwise DP heuristic */
+
+/* Replaces the PairAlign loop of HeuristicHPair::init (pastar/HeuristicHPair.cpp:47-61
+ * -> PairAlign.cpp:137-171): all N(N-1)/2 reverse DP tables in one launch,
+ * left device-resident.  kernel_ms (may be NULL) receives the CUDA-event time. */
+int pg_build_pair_tables(pg_ctx *ctx, float *kernel_ms);
+/* PairAlign::getScore (PairAlign.cpp:174-177) for a whole table: rows x cols int32, row-major. */
+int pg_pair_table_shape(const pg_ctx *ctx, int pair, int *rows, int *cols);
+int pg_copy_pair_table(pg_ctx *ctx, int pair, int32_t *out);
+/* HeuristicHPair::calculate_h<N> (HeuristicHPair.cpp:73-86) for n coords (n x N uint16). */
+int pg_calculate_h(pg_ctx *ctx, const uint16_t *coords, int64_t n, int32_t *out);
+
+/* ------------------------------------------------------------------ (3) owner hash */
+
+/* Coord<N>::configure_hash (pastar/CoordHash.cpp:260-265); default FZORDER / 12. */
+int pg_configure_hash(pg_ctx *ctx, int hash_type, int hash_shift);
+/* Coord<N>::get_id(size) (CoordHash.cpp:190-245) for n coords. */
+int pg_owner(pg_ctx *ctx, const uint16_t *coords, int64_t n, int size, uint32_t *out);
+
+/* ------------------------------------------------------------------ (2) batched expansion */
+
+/* Replaces Node<N>::getNeigh (pastar/Node.cpp:205-248) for k parents at once.
+ * parents: k records in pg_node layout (== Node<N>).  out_succ: room for
+ * k * (2^N - 1) records in pg_succ layout; parent i's successors start at
+ * record i * (2^N - 1), in ascending move-mask order, out_counts[i] of them
+ * (borderCheck-failing masks are not emitted, as in the reference). */
+int pg_expand_batch(pg_ctx *ctx, const void *parents, int64_t k, int vec_size, void *out_succ, int32_t *out_counts);
+int pg_expand_batch_dev(pg_ctx *ctx, const void *d_parents, int64_t k, int vec_size, void *d_out_succ,
+                        int32_t *d_out_counts, void *stream);
+
+/* ------------------------------------------------------------------ (3)+(4) search */
+
+typedef struct {
+    int32_t n_parts;        /* number of hash-owned partitions (= GPUs); 1 = single GPU          */
+    int32_t part;           /* this context's partition id                                       */
+    int64_t table_capacity; /* closed+open table slots (rounded up to a power of two); 0 = auto  */
+    int64_t batch_target;   /* frontier nodes popped per round (whole f-buckets, at least one); 0 = auto */
+    int64_t max_expansions; /* > 0: stop after this many expansions (budgeted run, not optimal)  */
+    int32_t rounds_per_sync;/* rounds launched between host checks; 0 = auto                     */
+    int32_t reserved;
+} pg_search_config;
+
+typedef struct {
+    int32_t finished;       /* 1 = optimal goal reached; 0 = budget hit                          */
+    int32_t g, f;           /* "Final Score" g and f (Node.cpp:41-47)                            */
+    int32_t align_len;      /* columns of the alignment                                          */
+    int64_t pops;           /* dequeues incl. stale ones: the reference's "Total" (PAStar.cpp:341) */
+    int64_t expansions;     /* nodes run through the getNeigh-equivalent                         */
+    int64_t generated;      /* successors produced (after borderCheck)                           */
+    int64_t reopen;         /* PAStar.cpp:231,347                                                */
+    int64_t open_size, closed_size;
+    int64_t rounds;
+    double seconds;         /* phase-2 wall time                                                 */
+    double kernel_ms;       /* CUDA-event time of the expansion kernels                          */
+} pg_result;
+
+/* Replaces PAStar<N>::pa_star (pastar/PAStar.cpp:626-673) on ONE GPU
+ * (cfg->n_parts must be 1): batched pop -> expand -> dedupe -> push until the
+ * optimality-preserving stop (PAStar.cpp:410-547: goal accepted only when no
+ * open node has f < g_goal).  rows (may be NULL): N buffers of at least
+ * sum(lens)+1 bytes receive the aligned sequences (backtrace.cpp:77-109). */
+int pg_search(pg_ctx *ctx, const pg_search_config *cfg, pg_result *res, char *const *rows);
+
+/* Step-wise form for hash-partitioned multi-GPU drivers (one context per GPU,
+ * the exchange between the two calls is the driver's: NCCL all-to-all).
+ * Replaces worker_inner's expand + reconciliation (PAStar.cpp:319-401) and
+ * sender/receiver (pastar_functions/PAStarSender.cpp, PAStarReceiver.cpp). */
+int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg);
+/* Pop up to batch_target nodes whose f < f_limit and expand them; successors
+ * owned by this partition are deduped and pushed, the others are appended to
+ * per-destination outboxes as pg_xrec records. */
+int pg_search_round(pg_ctx *ctx, int32_t f_limit);
+/* Device pointer + record count of the outbox for partition dst (valid until the next round). */
+int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count);
+/* Dedupe + push records received from other partitions (device pointer). */
+int pg_search_insert_dev(pg_ctx *ctx, const void *d_records, int64_t count);
+/* Local lower bound of open f (INT32_MAX when empty), best goal g seen here
+ * (INT32_MAX when none) and counters so far. */
+int pg_search_status(pg_ctx *ctx, int32_t *min_open_f, int32_t *best_goal_g, pg_result *counters);
+/* Closed/open table lookup for the distributed backtrace
+ * (pastar_functions/PAStarDistributedBacktrace.cpp:18-214): found=0 if absent. */
+int pg_search_lookup(pg_ctx *ctx, const uint16_t *pos, int32_t *found, int32_t *g, int32_t *parenti);
+int pg_search_end(pg_ctx *ctx);
+/* bytes per exchanged successor record for this context */
+int pg_xrec_stride(const pg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASTAR_GPU_H */

@@ -1,0 +1,286 @@
+// C ABI of libpastar_gpu (include/pastar_gpu.h): context management and the
+// host-pointer entry points.  No CPU fallback: every compute entry point
+// launches a CUDA kernel or fails.
+#include <algorithm>
+#include <cstring>
+
+#include "pg_internal.cuh"
+
+int pg_fail(pg_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
+
+extern "C" const char *pg_last_error(const pg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pg_stage(pg_ctx *ctx, int which, size_t bytes, void **out)
+{
+    if (ctx->stage_bytes[which] < bytes) {
+        if (ctx->d_stage[which]) cudaFree(ctx->d_stage[which]);
+        ctx->d_stage[which] = nullptr;
+        ctx->stage_bytes[which] = 0;
+        size_t want = std::max(bytes, (size_t)1 << 20);
+        PG_CUDA(ctx, cudaMalloc(&ctx->d_stage[which], want));
+        ctx->stage_bytes[which] = want;
+    }
+    *out = ctx->d_stage[which];
+    return PG_OK;
+}
+
+static bool supported_n(int n)
+{
+    return (n >= 3 && n <= 10) || n == 14 || n == 16; // max_seq_helper.h:9-19
+}
+
+extern "C" int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens, const int32_t *cost90x90, int gap_open,
+                             int gap_ext, int gap_gap, const int32_t *w_int, int device, pg_ctx **out)
+{
+    if (!out) return PG_ERR_ARG;
+    *out = nullptr;
+    if (!seqs || !lens || !supported_n(n_seq)) return PG_ERR_ARG;
+    for (int i = 0; i < n_seq; i++)
+        if (lens[i] < 1 || lens[i] > 65534 || !seqs[i]) return PG_ERR_ARG; // Coord is uint16 (Coord.h:68)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PG_ERR_CUDA; // no CPU fallback
+    pg_ctx *ctx = new pg_ctx();
+    if (device >= 0) {
+        if (cudaSetDevice(device) != cudaSuccess) {
+            delete ctx;
+            return PG_ERR_CUDA;
+        }
+    }
+    cudaGetDevice(&ctx->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) {
+        delete ctx;
+        return PG_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->n = n_seq;
+    ctx->npairs = n_seq * (n_seq - 1) / 2;
+    *out = ctx; // from here on errors leave a context whose message can be read; caller destroys it
+
+    DevProblem &dp = ctx->dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.n = n_seq;
+    dp.npairs = ctx->npairs;
+    dp.gap_open = gap_open;
+    dp.gap_ext = gap_ext;
+    dp.gap_gap = gap_gap;
+    dp.hash_type = PG_HASH_FZORDER; // CoordHash.cpp:17-18 defaults
+    dp.hash_shift = 12;
+
+    PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+
+    // residues: one arena, each sequence padded with a trailing 0 (Node.cpp:225 reads seq[len])
+    size_t seq_bytes = 0;
+    std::vector<size_t> seq_off(n_seq);
+    int max_len = 0;
+    for (int i = 0; i < n_seq; i++) {
+        ctx->len[i] = dp.len[i] = lens[i];
+        ctx->seqs.emplace_back(seqs[i], seqs[i] + lens[i]);
+        for (int j = 0; j < lens[i]; j++)
+            if ((unsigned char)seqs[i][j] >= 90)
+                return pg_fail(ctx, PG_ERR_ARG, "residue outside the 90x90 cost table (Cost.h:49: pam250['Z']['Z'])");
+        seq_off[i] = seq_bytes;
+        seq_bytes += ((size_t)lens[i] + 1 + 15) & ~size_t(15);
+        max_len = std::max(max_len, lens[i]);
+    }
+    std::vector<uint8_t> hseq(seq_bytes, 0);
+    for (int i = 0; i < n_seq; i++) memcpy(hseq.data() + seq_off[i], seqs[i], (size_t)lens[i]);
+    PG_CUDA(ctx, cudaMalloc(&ctx->d_seq, seq_bytes));
+    PG_CUDA(ctx, cudaMemcpy(ctx->d_seq, hseq.data(), seq_bytes, cudaMemcpyHostToDevice));
+    for (int i = 0; i < n_seq; i++) dp.seq[i] = ctx->d_seq + seq_off[i];
+
+    // cost table
+    std::vector<int32_t> hcost(90 * 90);
+    if (cost90x90)
+        memcpy(hcost.data(), cost90x90, sizeof(int32_t) * 8100);
+    else
+        pg_default_cost_table(hcost.data());
+    bool nonneg = gap_open >= 0 && gap_ext >= 0;
+    for (int32_t v : hcost) nonneg = nonneg && v >= 0;
+    PG_CUDA(ctx, cudaMalloc(&ctx->d_cost, sizeof(int32_t) * 8100));
+    PG_CUDA(ctx, cudaMemcpy(ctx->d_cost, hcost.data(), sizeof(int32_t) * 8100, cudaMemcpyHostToDevice));
+    dp.cost = ctx->d_cost;
+
+    // packed-key geometry
+    int kb = 1;
+    while ((1 << kb) <= max_len) kb++;
+    dp.key_bits = kb;
+    if (n_seq * kb > 128) return pg_fail(ctx, PG_ERR_UNSUPPORTED, "packed coordinate key exceeds 128 bits");
+
+    // pair geometry + table arena; a cell never exceeds the all-gaps path cost
+    long long bound = 0;
+    size_t cells = 0;
+    int k = 0;
+    for (int i = 0; i < n_seq - 1; i++) {
+        for (int j = i + 1; j < n_seq; j++, k++) { // HeuristicHPair.cpp:54-61 order
+            PairGeom g;
+            g.a = i;
+            g.b = j;
+            g.rows = lens[i] + 1;
+            g.cols = lens[j] + 1;
+            g.offset = cells;
+            cells += ((size_t)g.rows * g.cols + 127) & ~size_t(127);
+            ctx->pairs.push_back(g);
+            dp.pa[k] = (uint8_t)i;
+            dp.pb[k] = (uint8_t)j;
+            dp.cols[k] = g.cols;
+            dp.w[k] = w_int ? w_int[i * n_seq + j] : 1;
+            bound = std::max(bound, (long long)std::max(gap_open, gap_ext) * (lens[i] + lens[j]));
+        }
+    }
+    ctx->table_cells = cells;
+    dp.cell16 = (nonneg && bound < 65536) ? 1 : 0;
+    const size_t cell_bytes = dp.cell16 ? 2 : 4;
+    PG_CUDA(ctx, cudaMalloc(&ctx->d_tables, cells * cell_bytes));
+    for (int p = 0; p < ctx->npairs; p++) dp.table[p] = (const char *)ctx->d_tables + ctx->pairs[p].offset * cell_bytes;
+    return PG_OK;
+}
+
+extern "C" void pg_ctx_destroy(pg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    pg_search_free(ctx);
+    if (ctx->d_seq) cudaFree(ctx->d_seq);
+    if (ctx->d_cost) cudaFree(ctx->d_cost);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    for (int i = 0; i < 2; i++)
+        if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+
+extern "C" int pg_build_pair_tables(pg_ctx *ctx, float *kernel_ms)
+{
+    if (!ctx) return PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = pg_launch_pair_dp(ctx, kernel_ms);
+    if (rc == PG_OK) ctx->tables_built = true;
+    return rc;
+}
+
+extern "C" int pg_pair_table_shape(const pg_ctx *ctx, int pair, int *rows, int *cols)
+{
+    if (!ctx || pair < 0 || pair >= ctx->npairs || !rows || !cols) return PG_ERR_ARG;
+    *rows = ctx->pairs[pair].rows;
+    *cols = ctx->pairs[pair].cols;
+    return PG_OK;
+}
+
+extern "C" int pg_copy_pair_table(pg_ctx *ctx, int pair, int32_t *out)
+{
+    if (!ctx || pair < 0 || pair >= ctx->npairs || !out) return PG_ERR_ARG;
+    if (!ctx->tables_built) return pg_fail(ctx, PG_ERR_STATE, "pg_build_pair_tables has not run");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const PairGeom &g = ctx->pairs[pair];
+    const size_t n = (size_t)g.rows * g.cols;
+    if (ctx->dp.cell16) {
+        std::vector<uint16_t> tmp(n);
+        PG_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->dp.table[pair], n * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) out[i] = tmp[i];
+    } else {
+        PG_CUDA(ctx, cudaMemcpy(out, ctx->dp.table[pair], n * 4, cudaMemcpyDeviceToHost));
+    }
+    return PG_OK;
+}
+
+extern "C" int pg_calculate_h(pg_ctx *ctx, const uint16_t *coords, int64_t n, int32_t *out)
+{
+    if (!ctx || n < 0 || (n > 0 && (!coords || !out))) return PG_ERR_ARG;
+    if (!ctx->tables_built) return pg_fail(ctx, PG_ERR_STATE, "pg_build_pair_tables has not run");
+    if (n == 0) return PG_OK;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *d_in, *d_out;
+    int rc;
+    if ((rc = pg_stage(ctx, 0, (size_t)n * ctx->n * 2, &d_in)) != PG_OK) return rc;
+    if ((rc = pg_stage(ctx, 1, (size_t)n * 4, &d_out)) != PG_OK) return rc;
+    PG_CUDA(ctx, cudaMemcpyAsync(d_in, coords, (size_t)n * ctx->n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = pg_launch_calc_h(ctx, (const uint16_t *)d_in, n, (int32_t *)d_out, ctx->stream)) != PG_OK) return rc;
+    PG_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+extern "C" int pg_configure_hash(pg_ctx *ctx, int hash_type, int hash_shift)
+{
+    if (!ctx || hash_type < 0 || hash_type > 3) return PG_ERR_ARG;
+    if (hash_shift < 0 || hash_shift > 21) return pg_fail(ctx, PG_ERR_HASH_SHIFT, "Invalid Hash Shift"); // CoordHash.cpp:241
+    ctx->dp.hash_type = hash_type;
+    ctx->dp.hash_shift = hash_shift;
+    return PG_OK;
+}
+
+extern "C" int pg_owner(pg_ctx *ctx, const uint16_t *coords, int64_t n, int size, uint32_t *out)
+{
+    if (!ctx || n < 0 || size < 1 || (n > 0 && (!coords || !out))) return PG_ERR_ARG;
+    if (n == 0) return PG_OK;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *d_in, *d_out;
+    int rc;
+    if ((rc = pg_stage(ctx, 0, (size_t)n * ctx->n * 2, &d_in)) != PG_OK) return rc;
+    if ((rc = pg_stage(ctx, 1, (size_t)n * 4, &d_out)) != PG_OK) return rc;
+    PG_CUDA(ctx, cudaMemcpyAsync(d_in, coords, (size_t)n * ctx->n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = pg_launch_owner(ctx, (const uint16_t *)d_in, n, size, (uint32_t *)d_out, ctx->stream)) != PG_OK) return rc;
+    PG_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+extern "C" int pg_expand_batch_dev(pg_ctx *ctx, const void *d_parents, int64_t k, int vec_size, void *d_out_succ,
+                                   int32_t *d_out_counts, void *stream)
+{
+    if (!ctx || k < 0 || vec_size < 1 || vec_size > 64 || (k > 0 && (!d_parents || !d_out_succ || !d_out_counts))) return PG_ERR_ARG;
+    if (!ctx->tables_built) return pg_fail(ctx, PG_ERR_STATE, "pg_build_pair_tables has not run");
+    if (((uintptr_t)d_out_succ & 15) || ((uintptr_t)d_parents & 3)) return pg_fail(ctx, PG_ERR_ARG, "device buffers must be 16-byte aligned");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return pg_launch_expand(ctx, d_parents, k, vec_size, d_out_succ, d_out_counts, (cudaStream_t)stream); // NULL = the legacy default stream, as in CUDA
+}
+
+// Host-pointer form: chunks of parents are copied in, expanded and copied out,
+// two chunks in flight on two streams so copies overlap the kernel when the
+// host buffers are pinned.
+extern "C" int pg_expand_batch(pg_ctx *ctx, const void *parents, int64_t k, int vec_size, void *out_succ, int32_t *out_counts)
+{
+    if (!ctx || k < 0 || vec_size < 1 || vec_size > 64 || (k > 0 && (!parents || !out_succ || !out_counts))) return PG_ERR_ARG;
+    if (!ctx->tables_built) return pg_fail(ctx, PG_ERR_STATE, "pg_build_pair_tables has not run");
+    if (k == 0) return PG_OK;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nstride = pg_node_stride(ctx->n), sstride = pg_succ_stride(ctx->n);
+    const size_t S = ((size_t)1 << ctx->n) - 1;
+    // chunk so that one chunk's records are about 64 MiB
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / (S * sstride)));
+    chunk = std::min<int64_t>(chunk, k);
+    const size_t in_b = (size_t)chunk * nstride, out_b = (size_t)chunk * S * sstride, cnt_b = (size_t)chunk * 4;
+    const size_t in_off = 0, cnt_off = (in_b + 255) & ~size_t(255), out_off = (cnt_off + cnt_b + 255) & ~size_t(255);
+    const size_t per = out_off + out_b;
+    cudaStream_t st[2] = {ctx->stream, ctx->stream2};
+    char *buf[2];
+    int rc;
+    for (int i = 0; i < 2; i++) {
+        void *pbuf;
+        if ((rc = pg_stage(ctx, i, per, &pbuf)) != PG_OK) return rc;
+        buf[i] = (char *)pbuf;
+    }
+    int which = 0;
+    for (int64_t off = 0; off < k; off += chunk, which ^= 1) {
+        const int64_t m = std::min(chunk, k - off);
+        char *b = buf[which];
+        cudaStream_t s = st[which];
+        PG_CUDA(ctx, cudaMemcpyAsync(b + in_off, (const char *)parents + off * nstride, (size_t)m * nstride, cudaMemcpyHostToDevice, s));
+        if ((rc = pg_launch_expand(ctx, b + in_off, m, vec_size, b + out_off, (int32_t *)(b + cnt_off), s)) != PG_OK) return rc;
+        PG_CUDA(ctx, cudaMemcpyAsync((char *)out_succ + (size_t)off * S * sstride, b + out_off, (size_t)m * S * sstride,
+                                     cudaMemcpyDeviceToHost, s));
+        PG_CUDA(ctx, cudaMemcpyAsync(out_counts + off, b + cnt_off, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    }
+    PG_CUDA(ctx, cudaStreamSynchronize(st[0]));
+    PG_CUDA(ctx, cudaStreamSynchronize(st[1]));
+    return PG_OK;
+}

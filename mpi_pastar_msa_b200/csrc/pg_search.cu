@@ -1,0 +1,1295 @@
+// Kernels 3+ — the batched PA-Star search: per-GPU closed/open hash table,
+// f-indexed open buckets, batched pop, fused expand + owner + dedupe + push.
+//
+// Replaces, for one hash-owned partition (reference: one worker thread):
+//   PAStar<N>::worker_inner      pastar/PAStar.cpp:319-401   pop / closed check / expand / reconcile
+//   PAStar<N>::enqueue           pastar/PAStar.cpp:219-237   closed-list dedupe + reopen
+//   PriorityList<N>              pastar/include/PriorityList.h:84-122  (pos-unique, min-f pop)
+//   process_final_node/check_stop pastar/PAStar.cpp:410-547  optimality-preserving stop
+//
+// Data layout in HBM (all device resident, nothing per-node on the host):
+//   table   open-addressing hash table, one entry per coordinate ever generated:
+//             KEYW=1: {u64 key+1, u64 val}            16 B (two per 32 B sector)
+//             KEYW=2: {u64 key.lo+1.., u64 key.hi, u64 val, pad} 32 B
+//           key = coordinates packed key_bits each; val = ~(g<<32 | open<<31 | parenti)
+//           so a zeroed table is empty and "no g yet".  This is ClosedList and the
+//           pos-index of OpenList in one structure: best g per coordinate.
+//   buckets one u64 per f value {chunk offset, log2 size, fill}: the priority index of
+//           OpenList.  A bucket is a backward-linked list of chunks of u32 table slots
+//           whose sizes double (64, 128, ... 256 Ki entries), so a bucket of any size
+//           is a handful of contiguous runs; push = one atomicAdd, pop = whole chunks.
+//   plan    per round: the chunks selected by the select kernel.
+// A round is two launches on one stream: select (1 CTA) then expand (persistent
+// grid).  The host only reads the 128-byte control block every few rounds.
+//
+// Duplicate detection (the dominant cost): one 16 B load per successor; 90+ % of
+// successors are rejected right there (same key, g not better) without any
+// atomic or write.  New keys take one CAS on the key word; improvements one CAS
+// on the value word; only those are pushed to the open buckets.
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cstring>
+
+#include "pg_expand_core.cuh"
+
+namespace {
+
+constexpr uint32_t UNIT = 64;              // pool allocation unit (table slots); first chunk of a bucket
+constexpr uint32_t MAXLG = 12;             // largest chunk = UNIT << MAXLG slots
+constexpr uint32_t CHUNK_NONE = 0xffffffffu;
+constexpr uint32_t CNT_MASK = (1u << 27) - 1u;
+// bucket state: [63:32] chunk offset in units, [31:27] log2(chunk units), [26:0] fill
+__host__ __device__ constexpr unsigned long long bucket_pack(uint32_t off, uint32_t lg, uint32_t cnt)
+{
+    return ((unsigned long long)off << 32) | ((unsigned long long)lg << 27) | cnt;
+}
+constexpr unsigned long long BUCKET_EMPTY = ((unsigned long long)CHUNK_NONE << 32) | UNIT; // lg 0, "full": first push installs
+constexpr int SELECT_THREADS = 1024;
+constexpr int MAX_PROBE = 4096;
+constexpr uint64_t OPEN_BIT = 1ull << 31;  // in the un-inverted packing
+
+struct PlanEntry {
+    uint32_t unit, count, offset, start; // pool[unit*UNIT + start .. +count) are batch entries offset..offset+count
+};
+
+} // namespace
+
+struct SearchState {
+    int keyw = 1;
+    uint64_t cap = 0;        // slots (power of two)
+    uint64_t *d_table = nullptr;
+    unsigned long long *d_buckets = nullptr;
+    uint32_t *d_tail = nullptr;              // per bucket: entries in the chunks behind the head
+    uint32_t *d_pool = nullptr;
+    unsigned long long *d_link = nullptr;    // per unit: {offset, lg} of the previous chunk of the bucket
+    uint32_t n_units = 0;
+    PlanEntry *d_plan = nullptr;
+    uint32_t plan_cap = 0;
+    SearchCtrl *d_ctrl = nullptr;
+    SearchCtrl *h_ctrl = nullptr; // pinned
+    uint32_t *d_trace = nullptr;  // backtrace output
+    pg_search_config cfg;
+    int64_t batch_target = 0;
+    int f0 = 0, f_range = 0, ub = 0;
+    // multi-partition outboxes
+    char *d_outbox = nullptr;
+    unsigned long long *d_outbox_count = nullptr;
+    unsigned long long *h_outbox_count = nullptr;
+    uint64_t outbox_cap = 0; // records per destination
+    int xrec = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double kernel_ms = 0;
+    int64_t rounds = 0;
+    bool active = false;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// packed keys
+// ---------------------------------------------------------------------------------------------
+template <int KEYW>
+struct Key;
+template <>
+struct Key<1> {
+    unsigned long long lo;
+    __device__ __forceinline__ static Key zero() { return Key{0ull}; }
+    __device__ __forceinline__ void add_bit(int off) { lo += 1ull << off; }
+    __device__ __forceinline__ void add_val(unsigned v, int off) { lo += (unsigned long long)v << off; }
+    __device__ __forceinline__ Key plus(const Key &o) const { return Key{lo + o.lo}; }
+    __device__ __forceinline__ unsigned field(int off, unsigned m) const { return (unsigned)(lo >> off) & m; }
+    __device__ __forceinline__ unsigned long long hash() const
+    {
+        unsigned long long h = lo * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 32;
+        h *= 0xD6E8FEB86659FD93ull;
+        h ^= h >> 29;
+        return h;
+    }
+};
+template <>
+struct Key<2> {
+    unsigned long long lo, hi;
+    __device__ __forceinline__ static Key zero() { return Key{0ull, 0ull}; }
+    __device__ __forceinline__ void add_val(unsigned v, int off)
+    {
+        unsigned __int128 x = ((unsigned __int128)hi << 64) | lo;
+        x += (unsigned __int128)v << off;
+        lo = (unsigned long long)x;
+        hi = (unsigned long long)(x >> 64);
+    }
+    __device__ __forceinline__ void add_bit(int off) { add_val(1u, off); }
+    __device__ __forceinline__ Key plus(const Key &o) const
+    {
+        unsigned __int128 x = (((unsigned __int128)hi << 64) | lo) + (((unsigned __int128)o.hi << 64) | o.lo);
+        return Key{(unsigned long long)x, (unsigned long long)(x >> 64)};
+    }
+    __device__ __forceinline__ unsigned field(int off, unsigned m) const
+    {
+        unsigned __int128 x = ((unsigned __int128)hi << 64) | lo;
+        return (unsigned)(x >> off) & m;
+    }
+    __device__ __forceinline__ unsigned long long hash() const
+    {
+        unsigned long long h = (lo ^ (hi * 0xC2B2AE3D27D4EB4Full)) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 32;
+        h *= 0xD6E8FEB86659FD93ull;
+        h ^= h >> 29;
+        return h;
+    }
+};
+
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ld_cg_v2(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void cas128(unsigned long long *addr, unsigned long long n0, unsigned long long n1, unsigned long long &o0,
+                                       unsigned long long &o1)
+{ // compare with {0,0}
+    asm volatile(
+        "{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 n, {%5, %6};\n\t"
+        "atom.global.cas.b128 o, [%2], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(o0), "=l"(o1)
+        : "l"(addr), "l"(0ull), "l"(0ull), "l"(n0), "l"(n1)
+        : "memory");
+}
+
+struct DevSearch {
+    unsigned long long *table;
+    unsigned long long cap_mask;
+    unsigned long long *buckets;
+    uint32_t *tail;
+    uint32_t *pool;
+    unsigned long long *link;
+    uint32_t n_units;
+    unsigned long long goal_lo, goal_hi;
+    PlanEntry *plan;
+    uint32_t plan_cap;
+    SearchCtrl *ctrl;
+    int n_parts, part;
+    char *outbox;
+    unsigned long long *outbox_count;
+    unsigned long long outbox_cap;
+};
+
+struct Counters {
+    unsigned long long expansions, generated, reopen, inserted, pushed, pruned, stale;
+};
+
+// Find / claim the table slot of a key.  Returns the slot (entry index) or ~0 when the table is full.
+// Stored key words: KEYW=1 {lo + 1}; KEYW=2 {lo, hi | 1<<63} (n*key_bits <= 127), so 0 means empty.
+template <int KEYW>
+__device__ __forceinline__ unsigned long long table_slot(const DevSearch &d, const Key<KEYW> &key, unsigned long long &val, bool &fresh)
+{
+    constexpr int ES = KEYW == 1 ? 2 : 4;
+    unsigned long long slot = key.hash() & d.cap_mask;
+    fresh = false;
+    for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+        unsigned long long *e = d.table + slot * ES;
+        if constexpr (KEYW == 1) {
+            unsigned long long k, v;
+            ld_cg_v2(e, k, v);
+            if (k == key.lo + 1) {
+                val = v;
+                return slot;
+            }
+            if (k != 0) continue;
+            unsigned long long prev = atomicCAS(e, 0ull, key.lo + 1);
+            if (prev == 0) {
+                fresh = true;
+                val = 0;
+                return slot;
+            }
+            if (prev == key.lo + 1) {
+                val = ld_cg_u64(e + 1);
+                return slot;
+            }
+        } else {
+            unsigned long long k0, k1;
+            ld_cg_v2(e, k0, k1);
+            const unsigned long long want0 = key.lo, want1 = key.hi | (1ull << 63);
+            if (k0 == want0 && k1 == want1) {
+                val = ld_cg_u64(e + 2);
+                return slot;
+            }
+            if (k0 != 0 || k1 != 0) continue;
+            unsigned long long p0, p1;
+            cas128(e, want0, want1, p0, p1);
+            if (p0 == 0 && p1 == 0) {
+                fresh = true;
+                val = 0;
+                return slot;
+            }
+            if (p0 == want0 && p1 == want1) {
+                val = ld_cg_u64(e + 2);
+                return slot;
+            }
+        }
+    }
+    return ~0ull;
+}
+
+template <int KEYW>
+__device__ __forceinline__ unsigned long long *val_ptr(const DevSearch &d, unsigned long long slot)
+{
+    return d.table + slot * (KEYW == 1 ? 2 : 4) + (KEYW == 1 ? 1 : 2);
+}
+
+// Push a table slot on the open bucket of f.
+//   old fill < capacity : the slot is written in place
+//   old fill == capacity: this thread installs the next (twice as large) chunk
+//   old fill > capacity : an install is in flight; poll and retry
+__device__ __forceinline__ void bucket_push(const DevSearch &d, int f, uint32_t slot)
+{
+    SearchCtrl *c = d.ctrl;
+    int b = f - c->f0;
+    if (b < 0) b = 0; // cannot happen with a consistent heuristic; keep it poppable
+    if (b >= c->f_range) {
+        c->error = 3;
+        return;
+    }
+    unsigned long long *bk = d.buckets + b;
+    for (;;) {
+        const unsigned long long cur = ld_cg_u64(bk);
+        if (((uint32_t)cur & CNT_MASK) > (UNIT << (((uint32_t)cur >> 27) & 31u))) continue;
+        const unsigned long long st = atomicAdd(bk, 1ull);
+        const uint32_t cnt = (uint32_t)st & CNT_MASK, lg = ((uint32_t)st >> 27) & 31u, off = (uint32_t)(st >> 32);
+        const uint32_t capn = UNIT << lg;
+        if (cnt < capn) {
+            d.pool[(size_t)off * UNIT + cnt] = slot;
+            return;
+        }
+        if (cnt == capn) {
+            const uint32_t nlg = off == CHUNK_NONE ? 0u : min(lg + 1u, MAXLG);
+            const uint32_t nc = atomicAdd(&c->chunk_bump, 1u << nlg);
+            if ((unsigned long long)nc + (1u << nlg) > d.n_units) {
+                c->error = 2;
+                atomicExch(bk, bucket_pack(off, lg, capn)); // leave the bucket consistent
+                return;
+            }
+            d.link[nc] = ((unsigned long long)off << 32) | lg;
+            d.pool[(size_t)nc * UNIT] = slot;
+            if (off != CHUNK_NONE) atomicAdd(&d.tail[b], capn);
+            __threadfence();
+            atomicExch(bk, bucket_pack(nc, nlg, 1u));
+            return;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// select: pick the chunks to pop this round (one CTA)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_scan2(unsigned *a, unsigned *b2, int t)
+{
+    for (int off = 1; off < SELECT_THREADS; off <<= 1) {
+        const unsigned v = t >= off ? a[t - off] : 0;
+        const unsigned v2 = t >= off ? b2[t - off] : 0;
+        __syncthreads();
+        a[t] += v;
+        b2[t] += v2;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, long long target, int f_limit)
+{
+    __shared__ unsigned s_a[SELECT_THREADS];
+    __shared__ unsigned s_b[SELECT_THREADS];
+    __shared__ int s_first;
+    SearchCtrl *c = d.ctrl;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        c->batch_n = 0;
+        c->plan_n = 0;
+    }
+    if (c->done || c->error) return;
+    const int range = c->f_range;
+    const int limit_f = min(f_limit, c->best_goal);
+    const long long limit_b = (long long)limit_f - c->f0; // buckets >= limit_b are not popped
+    // ---- first non-empty bucket at or after the cursor
+    int cursor = c->cursor;
+    int first = -1;
+    while (cursor < range) {
+        if (t == 0) s_first = INT_MAX;
+        __syncthreads();
+        const int b = cursor + t;
+        if (b < range && (uint32_t)(d.buckets[b] >> 32) != CHUNK_NONE) atomicMin(&s_first, b);
+        __syncthreads();
+        first = s_first;
+        __syncthreads();
+        if (first != INT_MAX) break;
+        cursor += SELECT_THREADS;
+        first = -1;
+    }
+    if (first < 0) { // open list exhausted
+        if (t == 0) {
+            c->cursor = range;
+            c->min_open_f = INT_MAX;
+            if (d.n_parts == 1) c->done = 2;
+        }
+        return;
+    }
+    if (t == 0) {
+        c->cursor = first;
+        c->min_open_f = c->f0 + first;
+    }
+    if ((long long)first >= limit_b) { // every open node has f >= best goal (or the caller's limit)
+        if (t == 0 && d.n_parts == 1 && c->best_goal != INT_MAX && first >= c->best_goal - c->f0) c->done = 1;
+        return;
+    }
+    // ---- window of SELECT_THREADS buckets starting at `first`
+    const int b = first + t;
+    unsigned entries = 0, cnt = 0, lg = 0, off = CHUNK_NONE;
+    if (b < range && (long long)b < limit_b) {
+        const unsigned long long st = d.buckets[b];
+        off = (uint32_t)(st >> 32);
+        if (off != CHUNK_NONE) {
+            lg = ((uint32_t)st >> 27) & 31u;
+            cnt = min((uint32_t)st & CNT_MASK, UNIT << lg);
+            entries = cnt + d.tail[b];
+        }
+    }
+    s_a[t] = entries;
+    s_b[t] = 0;
+    __syncthreads();
+    block_scan2(s_a, s_b, t);
+    const unsigned before = s_a[t] - entries;
+    __syncthreads();
+    // A bucket is taken if the buckets before it did not reach the target; the one that
+    // crosses it gives exactly the missing entries, newest first (chunks are stacks: the
+    // top of the head chunk is popped and its fill lowered).
+    unsigned take_chunks = 0, take_entries = 0;
+    if (entries && (long long)before < target) {
+        const unsigned want = (unsigned)min((long long)entries, target - before);
+        take_entries = want;
+        take_chunks = 1;
+        unsigned got = min(cnt, want);
+        unsigned long long lk = d.link[off];
+        while (got < want) {
+            got += UNIT << (uint32_t)(lk & 31u);
+            take_chunks++;
+            lk = d.link[(uint32_t)(lk >> 32)];
+        }
+    }
+    s_a[t] = take_entries;
+    s_b[t] = take_chunks;
+    __syncthreads();
+    block_scan2(s_a, s_b, t);
+    unsigned e_off = s_a[t] - take_entries;
+    const unsigned p_off = s_b[t] - take_chunks;
+    const unsigned total_e = s_a[SELECT_THREADS - 1], total_p = s_b[SELECT_THREADS - 1];
+    if (total_p > d.plan_cap) {
+        if (t == 0) c->error = 2;
+        return;
+    }
+    if (take_chunks) {
+        uint32_t ch = off, chlg = lg;
+        unsigned left = take_entries, fill = cnt, remain = entries;
+        for (unsigned i = 0;; i++) {
+            const unsigned n = min(fill, left);
+            d.plan[p_off + i] = PlanEntry{ch, n, e_off, fill - n}; // entries [fill-n, fill) of the chunk
+            e_off += n;
+            left -= n;
+            remain -= n;
+            if (n < fill || remain == 0) { // this chunk keeps fill-n entries and stays the head
+                fill -= n;
+                break;
+            }
+            const unsigned long long lk = d.link[ch];
+            ch = (uint32_t)(lk >> 32);
+            chlg = (uint32_t)(lk & 31u);
+            fill = UNIT << chlg;
+            if (left == 0) break; // next chunk untouched: it becomes a full head
+        }
+        if (remain == 0) {
+            d.buckets[b] = BUCKET_EMPTY;
+            d.tail[b] = 0;
+        } else {
+            d.buckets[b] = bucket_pack(ch, chlg, fill);
+            d.tail[b] = remain - fill;
+        }
+    }
+    if (t == 0) {
+        c->batch_n = (int)total_e;
+        c->plan_n = (int)total_p;
+        c->pops += total_e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused expand + owner + dedupe + push
+// ---------------------------------------------------------------------------------------------
+template <int N, int KEYW>
+struct ProbeSink {
+    using C = ExpCfg<N>;
+    const DevSearch &d;
+    const DevProblem &p;
+    const Key<KEYW> *s_keyhigh; // shared: key delta of each high mask
+    Key<KEYW> klow;             // parent key + this lane's low mask bits
+    int limit;                  // prune successors with f >= limit
+    int goal_mask;              // the move mask that reaches the final coordinate from this parent (0 if none)
+    Counters &cn;
+    // owner plan (multi-partition)
+    int own_type, own_shift, own_nb;
+    int own_sh[8];
+
+    __device__ __forceinline__ void operator()(int mask, int idx, const int (&posn)[N], int gnew, int hnew)
+    {
+        (void)idx;
+        const int f = gnew + hnew;
+        cn.generated++;
+        const bool is_goal = mask == goal_mask;
+        if (is_goal) atomicMin(&d.ctrl->best_goal, gnew);
+        if (f >= limit && !is_goal) {
+            cn.pruned++;
+            return;
+        }
+        const Key<KEYW> key = klow.plus(s_keyhigh[mask >> C::A]);
+        if (d.n_parts > 1) {
+            unsigned own;
+            if (own_type == PG_HASH_FSUM) {
+                unsigned s = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++) s += posn[i];
+                own = (s >> own_shift) % (unsigned)d.n_parts;
+            } else if (own_type == PG_HASH_PSUM) {
+                own = ((unsigned)(posn[0] + posn[1]) >> own_shift) % (unsigned)d.n_parts;
+            } else {
+                unsigned w = 0;
+                for (int m = 0; m < own_nb; m++)
+                    if (own_sh[m] >= 0) w |= key.field(own_sh[m], 1u) << m;
+                own = w % (unsigned)d.n_parts;
+            }
+            if ((int)own != d.part) {
+                // remote successor: append {key, g, f, parenti} to the owner's outbox
+                const unsigned long long pos = atomicAdd(&d.outbox_count[own], 1ull);
+                if (pos >= d.outbox_cap) {
+                    d.ctrl->error = 4;
+                    return;
+                }
+                constexpr int XW = KEYW == 1 ? 3 : 4; // u64 words per record
+                unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) + ((size_t)own * d.outbox_cap + pos) * XW;
+                r[0] = key.lo;
+                if constexpr (KEYW == 2) r[1] = key.hi;
+                r[KEYW] = ((unsigned long long)(unsigned)gnew << 32) | (unsigned)f;
+                r[KEYW + 1] = (unsigned long long)(unsigned)mask;
+                return;
+            }
+        }
+        upsert(key, gnew, f, mask);
+    }
+
+    __device__ __forceinline__ void upsert(const Key<KEYW> &key, int gnew, int f, int mask)
+    {
+        unsigned long long val;
+        bool fresh;
+        const unsigned long long slot = table_slot<KEYW>(d, key, val, fresh);
+        if (slot == ~0ull) {
+            d.ctrl->error = 1;
+            return;
+        }
+        if (fresh) cn.inserted++;
+        unsigned long long *vp = val_ptr<KEYW>(d, slot);
+        const unsigned long long mine = ~(((unsigned long long)(unsigned)gnew << 32) | OPEN_BIT | (unsigned long long)(unsigned)mask);
+        for (;;) {
+            const unsigned g_old = (unsigned)((~val) >> 32); // 0xffffffff for a fresh entry
+            if ((unsigned)gnew >= g_old) return;             // PAStar.cpp:228 / PriorityList.h:109: not better, drop
+            const unsigned long long prev = atomicCAS(vp, val, mine);
+            if (prev == val) break;
+            val = prev;
+        }
+        if (val != 0 && !((~val) & OPEN_BIT)) cn.reopen++; // was closed with a worse g: PAStar.cpp:230-231
+        cn.pushed++;
+        bucket_push(d, f, (uint32_t)slot);
+    }
+};
+
+template <int N, int KEYW>
+__global__ void __launch_bounds__(256) search_expand_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
+                                                            int own_nb, int own_sh0, int own_sh1, int own_sh2, int own_sh3,
+                                                            int own_sh4, int own_sh5, int own_sh6, int own_sh7)
+{
+    using C = ExpCfg<N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PairMeta *meta = reinterpret_cast<PairMeta *>(smem_raw);
+    Key<KEYW> *s_keyhigh = reinterpret_cast<Key<KEYW> *>(smem_raw + ((sizeof(PairMeta) + 15) & ~size_t(15)));
+    int *s_groups = reinterpret_cast<int *>(s_keyhigh + C::H);
+    __shared__ unsigned long long s_cnt[7];
+    __shared__ int s_ctl[4];
+
+    SearchCtrl *c = d.ctrl;
+    if (threadIdx.x == 0) { // one reader, so the whole CTA takes the same early exit
+        s_ctl[0] = (c->done || c->error) ? 0 : c->batch_n;
+        s_ctl[1] = c->plan_n;
+        s_ctl[2] = min(c->prune_limit, c->best_goal);
+    }
+    __syncthreads();
+    const int batch_n = s_ctl[0];
+    if (batch_n == 0) return;
+    const int plan_n = s_ctl[1];
+    const int limit = s_ctl[2];
+
+    pg_load_pair_meta(p, meta);
+    for (int hi = threadIdx.x; hi < C::H; hi += blockDim.x) {
+        Key<KEYW> k = Key<KEYW>::zero();
+        for (int b = 0; b < C::HB; b++)
+            if ((hi >> b) & 1) k.add_bit((C::A + b) * p.key_bits);
+        s_keyhigh[hi] = k;
+    }
+    if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+
+    constexpr int GROUPS = 256 / C::LP;
+    const int grp = threadIdx.x / C::LP, sub = threadIdx.x % C::LP;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = C::LP == 32 ? 0xffffffffu : (((1u << C::LP) - 1u) << (lane & ~(C::LP - 1)));
+    int *s_grp = s_groups + grp * C::GROUP_INTS;
+    Counters cn = {0, 0, 0, 0, 0, 0, 0};
+    const unsigned fmask = (1u << p.key_bits) - 1u;
+
+    for (int base = blockIdx.x * GROUPS; base < batch_n; base += gridDim.x * GROUPS) {
+        const int bi = base + grp;
+        if (bi >= batch_n) continue;
+        // ---- lane 0 of the group: plan lookup, load the entry, claim it (closed check, PAStar.cpp:344-351)
+        unsigned long long klo = 0, khi = 0, val = 0;
+        int ok = 0;
+        if (sub == 0) {
+            int lo = 0, hi = plan_n - 1;
+            while (lo < hi) { // last entry with offset <= bi
+                const int mid = (lo + hi + 1) >> 1;
+                if ((int)d.plan[mid].offset <= bi)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const PlanEntry pe = d.plan[lo];
+            const uint32_t slot = d.pool[(size_t)pe.unit * UNIT + pe.start + (bi - pe.offset)];
+            unsigned long long *e = d.table + (size_t)slot * (KEYW == 1 ? 2 : 4);
+            // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion
+            const unsigned long long old = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
+            if (!(old & OPEN_BIT)) {
+                ok = 1;
+                val = ~old;
+                if constexpr (KEYW == 1) {
+                    klo = ld_cg_u64(e) - 1;
+                } else {
+                    klo = ld_cg_u64(e);
+                    khi = ld_cg_u64(e + 1) & ~(1ull << 63);
+                }
+            } else {
+                cn.stale++;
+            }
+        }
+        ok = __shfl_sync(gmask, ok, 0, C::LP);
+        if (!ok) continue;
+        klo = __shfl_sync(gmask, klo, 0, C::LP);
+        if constexpr (KEYW == 2) khi = __shfl_sync(gmask, khi, 0, C::LP);
+        val = __shfl_sync(gmask, val, 0, C::LP);
+        Key<KEYW> pkey;
+        pkey.lo = klo;
+        if constexpr (KEYW == 2) pkey.hi = khi;
+        const int g = (int)(unsigned)(val >> 32);
+        const int parenti = (int)(val & 0xffffu);
+        int pos[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) pos[i] = (int)pkey.field(i * p.key_bits, fmask);
+        // the goal is reached from this parent by moving every sequence that is one short of its end
+        int alive = 0, onestep = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            alive |= (pos[i] < p.len[i]) << i;
+            onestep |= (pos[i] + 1 == p.len[i]) << i;
+        }
+        if (alive == 0) continue; // the goal itself: never expanded (PAStar.cpp:353-357)
+        if (sub == 0) cn.expansions++;
+
+        Key<KEYW> klow = pkey;
+#pragma unroll
+        for (int i = 0; i < C::A; i++)
+            if ((sub >> i) & 1) klow.add_bit(i * p.key_bits);
+        ProbeSink<N, KEYW> sink{d, p, s_keyhigh, klow, limit, alive == onestep ? alive : 0, cn, p.hash_type, p.hash_shift, own_nb,
+                                {own_sh0, own_sh1, own_sh2, own_sh3, own_sh4, own_sh5, own_sh6, own_sh7}};
+        pg_expand_parent<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, sink);
+    }
+    // ---- counters: one atomic per CTA per counter
+    atomicAdd(&s_cnt[0], cn.expansions);
+    atomicAdd(&s_cnt[1], cn.generated);
+    atomicAdd(&s_cnt[2], cn.reopen);
+    atomicAdd(&s_cnt[3], cn.inserted);
+    atomicAdd(&s_cnt[4], cn.pushed);
+    atomicAdd(&s_cnt[5], cn.pruned);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&c->expansions, s_cnt[0]);
+        atomicAdd(&c->generated, s_cnt[1]);
+        atomicAdd(&c->reopen, s_cnt[2]);
+        atomicAdd(&c->inserted, s_cnt[3]);
+        atomicAdd(&c->pushed, s_cnt[4]);
+        atomicAdd(&c->pruned, s_cnt[5]);
+    }
+}
+
+// Records received from other partitions: dedupe + push (PAStar.cpp:240-250 consume_queue -> enqueue).
+template <int KEYW>
+__global__ void insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs, long long n)
+{
+    constexpr int XW = KEYW == 1 ? 3 : 4;
+    SearchCtrl *c = d.ctrl;
+    unsigned long long inserted = 0, pushed = 0, reopen = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long *r = recs + i * XW;
+        Key<KEYW> key;
+        key.lo = r[0];
+        if constexpr (KEYW == 2) key.hi = r[1];
+        const unsigned long long gf = r[KEYW], pm = r[KEYW + 1];
+        const int gnew = (int)(unsigned)(gf >> 32), f = (int)(unsigned)gf, mask = (int)(unsigned)pm;
+        bool is_goal = key.lo == d.goal_lo;
+        if constexpr (KEYW == 2) is_goal = is_goal && key.hi == d.goal_hi;
+        if (is_goal) atomicMin(&c->best_goal, gnew);
+        if (f >= min(c->prune_limit, c->best_goal) && !is_goal) continue;
+        unsigned long long val;
+        bool fresh;
+        const unsigned long long slot = table_slot<KEYW>(d, key, val, fresh);
+        if (slot == ~0ull) {
+            c->error = 1;
+            continue;
+        }
+        if (fresh) inserted++;
+        unsigned long long *vp = val_ptr<KEYW>(d, slot);
+        const unsigned long long mine = ~(((unsigned long long)(unsigned)gnew << 32) | OPEN_BIT | (unsigned long long)(unsigned)mask);
+        bool won = false;
+        for (;;) {
+            const unsigned g_old = (unsigned)((~val) >> 32);
+            if ((unsigned)gnew >= g_old) break;
+            const unsigned long long prev = atomicCAS(vp, val, mine);
+            if (prev == val) {
+                won = true;
+                break;
+            }
+            val = prev;
+        }
+        if (!won) continue;
+        if (val != 0 && !((~val) & OPEN_BIT)) reopen++;
+        pushed++;
+        bucket_push(d, f, (uint32_t)slot);
+    }
+    if (inserted) atomicAdd(&c->inserted, inserted);
+    if (pushed) atomicAdd(&c->pushed, pushed);
+    if (reopen) atomicAdd(&c->reopen, reopen);
+}
+
+// Seed: insert the start node (Sequences::get_initial_node, Sequences.cpp:70-77; PAStar.cpp:153).
+template <int KEYW>
+__global__ void seed_kernel(const __grid_constant__ DevSearch d, int f, int parenti, int as_goal_g)
+{
+    Key<KEYW> key = Key<KEYW>::zero();
+    unsigned long long val;
+    bool fresh;
+    const unsigned long long slot = table_slot<KEYW>(d, key, val, fresh);
+    *val_ptr<KEYW>(d, slot) = ~((0ull << 32) | OPEN_BIT | (unsigned long long)(unsigned)parenti);
+    bucket_push(d, f, (uint32_t)slot);
+    d.ctrl->inserted = 1;
+    d.ctrl->pushed = 1;
+    (void)as_goal_g;
+}
+
+// Cost of the all-sequences-advance path: a valid alignment, hence an upper bound on g*.
+__global__ void ub_kernel(const __grid_constant__ DevProblem p, int *out)
+{
+    __shared__ long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const int pr = threadIdx.x;
+    if (pr < p.npairs) {
+        const int x = p.pa[pr], y = p.pb[pr];
+        int maxlen = 0;
+        for (int i = 0; i < p.n; i++) maxlen = max(maxlen, p.len[i]);
+        long long sum = 0;
+        int prev_x = 1, prev_y = 1; // initial parenti = all ones (Sequences.cpp:75)
+        for (int t = 0; t < maxlen; t++) {
+            const int mx = t < p.len[x], my = t < p.len[y];
+            int c;
+            if (mx && my)
+                c = p.cost[(int)p.seq[x][t] * 90 + (int)p.seq[y][t]];
+            else if (mx)
+                c = prev_y != 0 ? p.gap_open : p.gap_ext;
+            else if (my)
+                c = prev_x != 0 ? p.gap_open : p.gap_ext;
+            else
+                c = p.gap_gap;
+            sum += (long long)c * p.w[pr];
+            prev_x = mx;
+            prev_y = my;
+        }
+        atomicAdd((unsigned long long *)&s_sum, (unsigned long long)sum);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *out = s_sum > INT_MAX - 1 ? INT_MAX - 1 : (int)s_sum;
+}
+
+// Walk parenti from the final coordinate to the origin (backtrace.cpp:44-69); one thread.
+template <int KEYW>
+__global__ void backtrace_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d, uint32_t *out, int max_cols)
+{
+    int pos[PG_MAX_SEQ];
+    for (int i = 0; i < p.n; i++) pos[i] = p.len[i];
+    int cols = 0;
+    int g_final = -1;
+    for (;;) {
+        bool origin = true;
+        Key<KEYW> key = Key<KEYW>::zero();
+        for (int i = 0; i < p.n; i++) {
+            if (pos[i]) origin = false;
+            key.add_val((unsigned)pos[i], i * p.key_bits);
+        }
+        if (origin || cols >= max_cols) break;
+        // read-only probe
+        constexpr int ES = KEYW == 1 ? 2 : 4;
+        unsigned long long slot = key.hash() & d.cap_mask;
+        unsigned long long val = 0;
+        bool found = false;
+        for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+            const unsigned long long *e = d.table + slot * ES;
+            if constexpr (KEYW == 1) {
+                if (e[0] == key.lo + 1) {
+                    val = e[1];
+                    found = true;
+                    break;
+                }
+                if (e[0] == 0) break;
+            } else {
+                unsigned long long w1 = 1ull << 63;
+                if constexpr (KEYW == 2) w1 |= key.hi;
+                if (e[0] == key.lo && e[1] == w1) {
+                    val = e[2];
+                    found = true;
+                    break;
+                }
+                if (e[0] == 0 && e[1] == 0) break;
+            }
+        }
+        if (!found) {
+            out[0] = 0xffffffffu;
+            return;
+        }
+        const unsigned long long v = ~val;
+        if (cols == 0) g_final = (int)(unsigned)(v >> 32);
+        const unsigned mask = (unsigned)(v & 0xffffu);
+        out[2 + cols] = mask;
+        cols++;
+        for (int i = 0; i < p.n; i++) pos[i] -= (mask >> i) & 1;
+    }
+    out[0] = (uint32_t)cols;
+    out[1] = (uint32_t)g_final;
+}
+
+// Host-side table lookup of one coordinate (distributed backtrace).
+template <int KEYW>
+__global__ void lookup_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d, const uint16_t *pos, int *out)
+{
+    Key<KEYW> key = Key<KEYW>::zero();
+    for (int i = 0; i < p.n; i++) key.add_val((unsigned)pos[i], i * p.key_bits);
+    constexpr int ES = KEYW == 1 ? 2 : 4;
+    unsigned long long slot = key.hash() & d.cap_mask;
+    out[0] = 0;
+    for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+        const unsigned long long *e = d.table + slot * ES;
+        bool hit, empty;
+        unsigned long long val;
+        if constexpr (KEYW == 1) {
+            hit = e[0] == key.lo + 1;
+            empty = e[0] == 0;
+            val = e[1];
+        } else {
+            unsigned long long w1 = 1ull << 63;
+            if constexpr (KEYW == 2) w1 |= key.hi;
+            hit = e[0] == key.lo && e[1] == w1;
+            empty = e[0] == 0 && e[1] == 0;
+            val = e[2];
+        }
+        if (hit) {
+            const unsigned long long v = ~val;
+            out[0] = 1;
+            out[1] = (int)(unsigned)(v >> 32);
+            out[2] = (int)(v & 0xffffu);
+            out[3] = (v & OPEN_BIT) ? 1 : 0;
+            return;
+        }
+        if (empty) return;
+    }
+}
+
+// Count open / closed entries at the end (PAStar.cpp:591-619 report).
+template <int KEYW>
+__global__ void census_kernel(const __grid_constant__ DevSearch d, unsigned long long *out)
+{
+    constexpr int ES = KEYW == 1 ? 2 : 4;
+    unsigned long long open = 0, closed = 0;
+    const unsigned long long cap = d.cap_mask + 1;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long *e = d.table + i * ES;
+        const bool live = KEYW == 1 ? e[0] != 0 : (e[0] != 0 || e[1] != 0);
+        if (!live) continue;
+        const unsigned long long v = ~e[KEYW == 1 ? 1 : 2];
+        if (e[KEYW == 1 ? 1 : 2] == 0) continue; // claimed but never valued
+        if (v & OPEN_BIT)
+            open++;
+        else
+            closed++;
+    }
+    for (int o = 16; o; o >>= 1) {
+        open += __shfl_down_sync(0xffffffffu, open, o);
+        closed += __shfl_down_sync(0xffffffffu, closed, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (open) atomicAdd(out, open);
+        if (closed) atomicAdd(out + 1, closed);
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int ilog2i(int v)
+{
+    int l = 0;
+    while ((1 << (l + 1)) <= v) l++;
+    return l;
+}
+
+DevSearch dev_search(const pg_ctx *ctx)
+{
+    const SearchState *s = ctx->search;
+    DevSearch d;
+    d.table = (unsigned long long *)s->d_table;
+    d.cap_mask = s->cap - 1;
+    d.buckets = s->d_buckets;
+    d.tail = s->d_tail;
+    d.pool = s->d_pool;
+    d.link = s->d_link;
+    d.n_units = s->n_units;
+    {   // packed key of the final coordinate (Sequences::get_final_coord, Sequences.cpp:53-60)
+        unsigned __int128 k = 0;
+        for (int i = 0; i < ctx->n; i++) k += (unsigned __int128)(unsigned)ctx->len[i] << (i * ctx->dp.key_bits);
+        d.goal_lo = (unsigned long long)k;
+        d.goal_hi = (unsigned long long)(k >> 64);
+    }
+    d.plan = s->d_plan;
+    d.plan_cap = s->plan_cap;
+    d.ctrl = s->d_ctrl;
+    d.n_parts = s->cfg.n_parts;
+    d.part = s->cfg.part;
+    d.outbox = s->d_outbox;
+    d.outbox_count = s->d_outbox_count;
+    d.outbox_cap = s->outbox_cap;
+    return d;
+}
+
+template <int N, int KEYW>
+int launch_expand_round(pg_ctx *ctx, cudaStream_t st)
+{
+    using C = ExpCfg<N>;
+    SearchState *s = ctx->search;
+    constexpr int GROUPS = 256 / C::LP;
+    const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
+    static int occ = 0;
+    if (!occ) {
+        PG_CUDA(ctx, cudaFuncSetAttribute(search_expand_kernel<N, KEYW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_expand_kernel<N, KEYW>, 256, smem));
+        if (occ < 1) occ = 1;
+    }
+    // persistent grid: resident CTAs per SM x SM count, capped by the work of a full batch
+    long long grid = (long long)ctx->sm_count * occ;
+    const long long want = (s->batch_target + GROUPS - 1) / GROUPS;
+    if (grid > want) grid = std::max<long long>(1, want);
+    int sh[8];
+    const int nd = ctx->dp.hash_type == PG_HASH_PZORDER ? 2 : ctx->n;
+    for (int m = 0; m < 8; m++) {
+        const int q = ctx->dp.hash_shift + m;
+        const int coord = q % nd, bit = q / nd;
+        sh[m] = bit < ctx->dp.key_bits ? coord * ctx->dp.key_bits + bit : -1;
+    }
+    const int nb = std::min(8, ilog2i(std::max(1, s->cfg.n_parts)) + 2);
+    search_expand_kernel<N, KEYW><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, dev_search(ctx), nb, sh[0], sh[1], sh[2], sh[3], sh[4], sh[5],
+                                                                     sh[6], sh[7]);
+    PG_CUDA(ctx, cudaGetLastError());
+    return PG_OK;
+}
+
+template <int KEYW>
+int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st)
+{
+    switch (ctx->n) {
+#define CASE(X) \
+    case X:     \
+        return launch_expand_round<X, KEYW>(ctx, st);
+        CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(14) CASE(16)
+#undef CASE
+    }
+    return pg_fail(ctx, PG_ERR_ARG, "unsupported number of sequences");
+}
+
+int launch_round(pg_ctx *ctx, int f_limit)
+{
+    SearchState *s = ctx->search;
+    select_kernel<<<1, SELECT_THREADS, 0, ctx->stream>>>(dev_search(ctx), (long long)s->batch_target, f_limit);
+    PG_CUDA(ctx, cudaGetLastError());
+    int rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
+    s->rounds++;
+    return rc;
+}
+
+int sync_ctrl(pg_ctx *ctx)
+{
+    SearchState *s = ctx->search;
+    PG_CUDA(ctx, cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(SearchCtrl), cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    switch (s->h_ctrl->error) {
+    case 0:
+        return PG_OK;
+    case 1:
+        return pg_fail(ctx, PG_ERR_CAPACITY, "closed/open hash table is full: raise pg_search_config.table_capacity");
+    case 2:
+        return pg_fail(ctx, PG_ERR_CAPACITY, "open-list chunk pool exhausted: raise pg_search_config.table_capacity");
+    case 3:
+        return pg_fail(ctx, PG_ERR_CAPACITY, "f exceeded the bucket range");
+    default:
+        return pg_fail(ctx, PG_ERR_CAPACITY, "outbox overflow: lower batch_target");
+    }
+}
+
+void fill_counters(const SearchState *s, pg_result *r)
+{
+    const SearchCtrl *c = s->h_ctrl;
+    r->pops = (int64_t)c->pops;
+    r->expansions = (int64_t)c->expansions;
+    r->generated = (int64_t)c->generated;
+    r->reopen = (int64_t)c->reopen;
+    r->rounds = s->rounds;
+    r->kernel_ms = s->kernel_ms;
+}
+
+} // namespace
+
+void pg_search_free(pg_ctx *ctx)
+{
+    SearchState *s = ctx->search;
+    if (!s) return;
+    cudaFree(s->d_table);
+    cudaFree(s->d_buckets);
+    cudaFree(s->d_tail);
+    cudaFree(s->d_pool);
+    cudaFree(s->d_link);
+    cudaFree(s->d_plan);
+    cudaFree(s->d_ctrl);
+    cudaFree(s->d_trace);
+    cudaFree(s->d_outbox);
+    cudaFree(s->d_outbox_count);
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->h_outbox_count) cudaFreeHost(s->h_outbox_count);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+    ctx->search = nullptr;
+}
+
+extern "C" int pg_xrec_stride(const pg_ctx *ctx)
+{
+    if (!ctx) return 0;
+    return ctx->n * ctx->dp.key_bits <= 63 ? 24 : 32;
+}
+
+extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
+{
+    if (!ctx || !cfg || cfg->n_parts < 1 || cfg->n_parts > 64 || cfg->part < 0 || cfg->part >= cfg->n_parts) return PG_ERR_ARG;
+    if (!ctx->tables_built) return pg_fail(ctx, PG_ERR_STATE, "pg_build_pair_tables has not run");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    pg_search_free(ctx);
+    SearchState *s = new SearchState();
+    ctx->search = s;
+    s->cfg = *cfg;
+    s->keyw = ctx->n * ctx->dp.key_bits <= 63 ? 1 : 2;
+    if (s->keyw == 2 && ctx->n * ctx->dp.key_bits > 127) return pg_fail(ctx, PG_ERR_UNSUPPORTED, "packed coordinate key exceeds 127 bits");
+    s->xrec = pg_xrec_stride(ctx);
+    const size_t entry = s->keyw == 1 ? 16 : 32;
+
+    // ---- capacity: explicit, or a fraction of the free memory
+    size_t free_b = 0, total_b = 0;
+    PG_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    uint64_t cap = cfg->table_capacity > 0 ? (uint64_t)cfg->table_capacity : 0;
+    if (cap == 0) {
+        cap = 1;
+        while (cap * 2 * (entry + 8) <= free_b / 2 && cap * 2 <= (1ull << 32)) cap *= 2; // about half of what is free
+    } else {
+        uint64_t c2 = 1024;
+        while (c2 < cap) c2 *= 2;
+        cap = c2;
+    }
+    if (cap > (1ull << 32)) cap = 1ull << 32; // u32 slot ids in the open buckets
+    s->cap = cap;
+
+    s->batch_target = cfg->batch_target > 0 ? cfg->batch_target : 16384;
+
+    // ---- f range: [h(start), cost of the all-advance path]
+    int *d_tmp;
+    PG_CUDA(ctx, cudaMalloc(&d_tmp, 64));
+    std::vector<uint16_t> zero(ctx->n, 0);
+    uint16_t *d_zero;
+    PG_CUDA(ctx, cudaMalloc(&d_zero, 64));
+    PG_CUDA(ctx, cudaMemcpy(d_zero, zero.data(), ctx->n * 2, cudaMemcpyHostToDevice));
+    int rc = pg_launch_calc_h(ctx, d_zero, 1, d_tmp, ctx->stream);
+    if (rc != PG_OK) return rc;
+    ub_kernel<<<1, 128, 0, ctx->stream>>>(ctx->dp, d_tmp + 1);
+    PG_CUDA(ctx, cudaGetLastError());
+    int h2[2];
+    PG_CUDA(ctx, cudaMemcpyAsync(h2, d_tmp, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_tmp);
+    cudaFree(d_zero);
+    s->f0 = h2[0];
+    s->ub = h2[1];
+    long long range = (long long)s->ub - s->f0 + 2;
+    if (range < 2) range = 2;
+    if (range > (1ll << 27)) range = 1ll << 27; // 1 GiB of bucket heads at most; deeper f is pruned
+    s->f_range = (int)range;
+
+    // ---- allocations
+    PG_CUDA(ctx, cudaMalloc(&s->d_table, cap * entry));
+    PG_CUDA(ctx, cudaMemsetAsync(s->d_table, 0, cap * entry, ctx->stream));
+    PG_CUDA(ctx, cudaMalloc(&s->d_buckets, (size_t)s->f_range * 8));
+    PG_CUDA(ctx, cudaMalloc(&s->d_tail, (size_t)s->f_range * 4));
+    PG_CUDA(ctx, cudaMemsetAsync(s->d_tail, 0, (size_t)s->f_range * 4, ctx->stream));
+    fill_u64_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(s->d_buckets, BUCKET_EMPTY, (long long)s->f_range);
+    PG_CUDA(ctx, cudaGetLastError());
+    // Every table slot is pushed once per improvement.  Chunk sizes double, so a bucket wastes at most its own
+    // size; each non-empty bucket holds at least one unit.
+    uint64_t units = 2 * (cap / UNIT) + (uint64_t)s->f_range + 4096;
+    s->n_units = (uint32_t)std::min<uint64_t>(units, 0x7ffffff0ull);
+    PG_CUDA(ctx, cudaMalloc(&s->d_pool, (size_t)s->n_units * UNIT * 4));
+    PG_CUDA(ctx, cudaMalloc(&s->d_link, (size_t)s->n_units * 8));
+    // a round pops at most ~2*target entries: the bucket crossing the target may add one chunk of up to the
+    // entries already taken.  Plan entries: one per chunk.
+    s->plan_cap = (uint32_t)(SELECT_THREADS * (MAXLG + 4) + 64);
+    PG_CUDA(ctx, cudaMalloc(&s->d_plan, (size_t)s->plan_cap * sizeof(PlanEntry)));
+    PG_CUDA(ctx, cudaMalloc(&s->d_ctrl, sizeof(SearchCtrl)));
+    PG_CUDA(ctx, cudaMallocHost(&s->h_ctrl, sizeof(SearchCtrl)));
+    {
+        size_t total = 0;
+        for (int i = 0; i < ctx->n; i++) total += (size_t)ctx->len[i];
+        PG_CUDA(ctx, cudaMalloc(&s->d_trace, std::max<size_t>(1u << 16, (total + 64) * 4)));
+    }
+    PG_CUDA(ctx, cudaEventCreate(&s->ev0));
+    PG_CUDA(ctx, cudaEventCreate(&s->ev1));
+    if (cfg->n_parts > 1) {
+        // worst case every successor of a full batch goes to one destination
+        const uint64_t S = (1ull << ctx->n) - 1;
+        s->outbox_cap = (uint64_t)(s->batch_target + UNIT) * S;
+        PG_CUDA(ctx, cudaMalloc(&s->d_outbox, (size_t)cfg->n_parts * s->outbox_cap * s->xrec));
+        PG_CUDA(ctx, cudaMalloc(&s->d_outbox_count, 8 * 64));
+        PG_CUDA(ctx, cudaMallocHost(&s->h_outbox_count, 8 * 64));
+        PG_CUDA(ctx, cudaMemsetAsync(s->d_outbox_count, 0, 8 * 64, ctx->stream));
+    }
+
+    SearchCtrl c;
+    memset(&c, 0, sizeof(c));
+    c.f0 = s->f0;
+    c.f_range = s->f_range;
+    c.cursor = 0;
+    c.best_goal = INT_MAX;
+    c.prune_limit = (int)std::min<long long>((long long)s->ub + 1, (long long)s->f0 + s->f_range);
+    c.min_open_f = s->f0;
+    PG_CUDA(ctx, cudaMemcpyAsync(s->d_ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, ctx->stream));
+    // PAStar.cpp:153 enqueues the start node on rank 0 / OpenList[0] whatever its owner; here its true owner
+    // (get_id of the origin is 0 for every hash) which is partition 0 as well.
+    if (cfg->part == 0) {
+        const int parenti = (1 << ctx->n) - 1; // Sequences.cpp:75
+        if (s->keyw == 1)
+            seed_kernel<1><<<1, 1, 0, ctx->stream>>>(dev_search(ctx), s->f0, parenti, 0);
+        else
+            seed_kernel<2><<<1, 1, 0, ctx->stream>>>(dev_search(ctx), s->f0, parenti, 0);
+        PG_CUDA(ctx, cudaGetLastError());
+    }
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s->active = true;
+    return PG_OK;
+}
+
+extern "C" int pg_search_round(pg_ctx *ctx, int32_t f_limit)
+{
+    if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SearchState *s = ctx->search;
+    if (s->cfg.n_parts > 1) PG_CUDA(ctx, cudaMemsetAsync(s->d_outbox_count, 0, 8 * 64, ctx->stream));
+    int rc = launch_round(ctx, f_limit);
+    if (rc != PG_OK) return rc;
+    if (s->cfg.n_parts > 1)
+        PG_CUDA(ctx, cudaMemcpyAsync(s->h_outbox_count, s->d_outbox_count, 8 * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_ctrl(ctx);
+}
+
+extern "C" int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count)
+{
+    if (!ctx || !ctx->search || !d_records || !count) return PG_ERR_ARG;
+    SearchState *s = ctx->search;
+    if (dst < 0 || dst >= s->cfg.n_parts || s->cfg.n_parts < 2) return PG_ERR_ARG;
+    *d_records = s->d_outbox + (size_t)dst * s->outbox_cap * s->xrec;
+    *count = (int64_t)s->h_outbox_count[dst];
+    return PG_OK;
+}
+
+extern "C" int pg_search_insert_dev(pg_ctx *ctx, const void *d_records, int64_t count)
+{
+    if (!ctx || !ctx->search || count < 0 || (count > 0 && !d_records)) return PG_ERR_ARG;
+    if (count == 0) return PG_OK;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SearchState *s = ctx->search;
+    const long long grid = std::min<long long>((count + 255) / 256, (long long)ctx->sm_count * 8);
+    if (s->keyw == 1)
+        insert_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)d_records, (long long)count);
+    else
+        insert_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)d_records, (long long)count);
+    PG_CUDA(ctx, cudaGetLastError());
+    return sync_ctrl(ctx);
+}
+
+extern "C" int pg_search_status(pg_ctx *ctx, int32_t *min_open_f, int32_t *best_goal_g, pg_result *counters)
+{
+    if (!ctx || !ctx->search) return PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SearchState *s = ctx->search;
+    // a select with target 0 pops nothing but refreshes cursor / min_open_f
+    select_kernel<<<1, SELECT_THREADS, 0, ctx->stream>>>(dev_search(ctx), 0ll, INT_MIN + 1);
+    PG_CUDA(ctx, cudaGetLastError());
+    int rc = sync_ctrl(ctx);
+    if (rc != PG_OK) return rc;
+    if (min_open_f) *min_open_f = s->h_ctrl->min_open_f;
+    if (best_goal_g) *best_goal_g = s->h_ctrl->best_goal;
+    if (counters) {
+        memset(counters, 0, sizeof(*counters));
+        fill_counters(s, counters);
+    }
+    return PG_OK;
+}
+
+extern "C" int pg_search_lookup(pg_ctx *ctx, const uint16_t *pos, int32_t *found, int32_t *g, int32_t *parenti)
+{
+    if (!ctx || !ctx->search || !pos || !found) return PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SearchState *s = ctx->search;
+    uint16_t *d_pos = (uint16_t *)s->d_trace;
+    int *d_out = (int *)(s->d_trace + 64);
+    PG_CUDA(ctx, cudaMemcpyAsync(d_pos, pos, ctx->n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if (s->keyw == 1)
+        lookup_kernel<1><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), d_pos, d_out);
+    else
+        lookup_kernel<2><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), d_pos, d_out);
+    PG_CUDA(ctx, cudaGetLastError());
+    int h[4];
+    PG_CUDA(ctx, cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *found = h[0];
+    if (g) *g = h[1];
+    if (parenti) *parenti = h[2];
+    return PG_OK;
+}
+
+extern "C" int pg_search_end(pg_ctx *ctx)
+{
+    if (!ctx) return PG_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    pg_search_free(ctx);
+    return PG_OK;
+}
+
+extern "C" int pg_search(pg_ctx *ctx, const pg_search_config *cfg_in, pg_result *res, char *const *rows)
+{
+    if (!ctx || !res) return PG_ERR_ARG;
+    pg_search_config cfg;
+    if (cfg_in)
+        cfg = *cfg_in;
+    else
+        memset(&cfg, 0, sizeof(cfg));
+    if (cfg.n_parts == 0) cfg.n_parts = 1;
+    if (cfg.n_parts != 1) return pg_fail(ctx, PG_ERR_ARG, "pg_search runs one partition; use the step-wise calls for n_parts > 1");
+    memset(res, 0, sizeof(*res));
+    res->g = res->f = -1;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = pg_search_begin(ctx, &cfg);
+    if (rc != PG_OK) return rc;
+    SearchState *s = ctx->search;
+    const int per_sync = cfg.rounds_per_sync > 0 ? cfg.rounds_per_sync : 8;
+    PG_CUDA(ctx, cudaEventRecord(s->ev0, ctx->stream));
+    for (;;) {
+        for (int r = 0; r < per_sync; r++)
+            if ((rc = launch_round(ctx, INT_MAX)) != PG_OK) return rc;
+        if ((rc = sync_ctrl(ctx)) != PG_OK) return rc;
+        if (s->h_ctrl->done) break;
+        if (cfg.max_expansions > 0 && (int64_t)s->h_ctrl->expansions >= cfg.max_expansions) break;
+    }
+    PG_CUDA(ctx, cudaEventRecord(s->ev1, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    PG_CUDA(ctx, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->kernel_ms = ms;
+    fill_counters(s, res);
+    res->finished = s->h_ctrl->done == 1 ? 1 : 0;
+
+    // ---- open / closed census (the reference's final report, PAStar.cpp:591-619)
+    {
+        unsigned long long *d_cnt = (unsigned long long *)s->d_trace;
+        PG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
+        if (s->keyw == 1)
+            census_kernel<1><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
+        else
+            census_kernel<2><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
+        unsigned long long h[2];
+        PG_CUDA(ctx, cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        res->open_size = (int64_t)h[0];
+        res->closed_size = (int64_t)h[1];
+    }
+
+    if (res->finished) {
+        res->g = res->f = s->h_ctrl->best_goal; // h(goal) = 0
+        int total = 0;
+        for (int i = 0; i < ctx->n; i++) total += ctx->len[i];
+        if (s->keyw == 1)
+            backtrace_kernel<1><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), s->d_trace, total);
+        else
+            backtrace_kernel<2><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), s->d_trace, total);
+        PG_CUDA(ctx, cudaGetLastError());
+        std::vector<uint32_t> tr((size_t)total + 2);
+        PG_CUDA(ctx, cudaMemcpyAsync(tr.data(), s->d_trace, tr.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (tr[0] == 0xffffffffu) return pg_fail(ctx, PG_ERR_STATE, "backtrace lost the parent chain");
+        const int cols = (int)tr[0];
+        res->align_len = cols;
+        if ((int)tr[1] != res->g) return pg_fail(ctx, PG_ERR_STATE, "goal entry does not hold the best goal cost");
+        if (rows) {
+            // masks are stored goal-first; emit columns origin-first (backtrace.cpp:54-66)
+            std::vector<int> pos(ctx->n, 0);
+            for (int i = 0; i < ctx->n; i++) rows[i][cols] = 0;
+            for (int c = 0; c < cols; c++) {
+                const uint32_t mask = tr[2 + (cols - 1 - c)];
+                for (int i = 0; i < ctx->n; i++) {
+                    if ((mask >> i) & 1)
+                        rows[i][c] = ctx->seqs[i][pos[i]++];
+                    else
+                        rows[i][c] = '-';
+                }
+            }
+        }
+    }
+    res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return PG_OK;
+}

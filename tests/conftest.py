@@ -1,0 +1,144 @@
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+AA = "ACDEFGHIKLMNPQRSTVWY"  # the 20 letters with fully populated PAM rows
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: takes more than a few seconds")
+
+
+def random_seqs(n, length, seed):
+    """i.i.d. uniform protein sequences, the S7 / S8 generator (python random.seed(seed), choice)."""
+    r = random.Random(seed)
+    return ["".join(r.choice(AA) for _ in range(length)) for _ in range(n)]
+
+
+def family_seqs(n, length, seed, sub=0.08, indel=0.02):
+    """Related family: one random ancestor, per-sequence substitutions and a few indels (terminates under A*)."""
+    r = random.Random(seed)
+    anc = [r.choice(AA) for _ in range(length)]
+    out = []
+    for _ in range(n):
+        s = []
+        for c in anc:
+            x = r.random()
+            if x < indel:
+                continue
+            if x < 2 * indel:
+                s.append(r.choice(AA))
+            s.append(r.choice(AA) if r.random() < sub else c)
+        out.append("".join(s))
+    return out
+
+
+# the reference's four FASTA fixtures, restated as data so that nothing reads /root/reference at run time
+FIXTURES = {
+    "test": ["AAAA", "AAAB", "AABA", "AABB", "ABBA", "ABBB", "BBBA", "BBBB"],
+    "test2": ["AAAABBBBAAAAABBBBBAAAAAA", "AABBBBBBBBBBBBBBBBBBBBBB", "ABBAAAAAAAAAAAAAAAAAAAAA", "BBBBBBBBBBBBBBBBBBBBBBAA",
+              "BBBBBBCCCCCCCAAAAAAAAAAA"],
+    "PF08184": ["QAVRYANGYTYDIETGQVSSPYTGRVYETKGKAPFYGFGFEHPYHYYPGYYHGYPHAFY",
+                "QAVRYADGYTYDIETGQVSSPYTGRVYETKGKAPFYGFGFEHPYHYYPGYYHGYPHAFY",
+                "QAVRYANGYTYDIETGQVSSPYTGRVYETKGKAPFYGFGFKYPYHYYPGYYHGYPHVFY"],
+    "kinase": [
+        "NYIFGRTLGAGSFGVVRQARKLSTNEDVAIKILLKKALQGNNVQLQMLYEELSILQKLSHPNIVSFKDWFESKDKFYIVTQLATGGELFDRILSRGKFTEVDAVEIIVQILGAVEYMHSKNVVHRDLKPENVLYVDKSENSPLVIADFGIAKQLKGEEDLIYKAAGSLGYVAPEVLTQDGHGKPCDIWSIGVITYTLLCGYSPFIAESVEGFMEECTASRYPVTFHMPYWDNISIDVKRFILKALRLNPADRPTATELLDDPWITSK",
+        "DFEILKVIGRGAFSEVAVVKMKQTGQVYAMKIMNKWDMLKRGEVSCFREERDVLVNGDRRWITQLHFAFQDENYLYLVMEYYVGGDLLTLLSKFGERIPAEMARFYLAEIVMAIDSVHRLGYVHRDIKPDNILLDRCGHIRLADFGSCLKLRADGTVRSLVAVGTPDYLSPEILQAVGGGPGTGSYGPECDWWALGVFAYEMFYGQTPFYADSTAETYGKIVHYKEHLSLPLVDEGVPEEARDFIQRLLCPPETRLGRGGAGDFRTHPFFFGLDWD",
+        "TRKFKVELGRGESGTVYKGVLEDDRHVAVKKLENVRQGKEVFQAELSVIGRINHMNLVRIWGFCSEGSHRLLVSEYVENGSLANILFSEGGNILLDWEGRFNIALGVAKGLAYLHHECLEWVIHCDVKPENILLDQAFEPKITDFGLVKLLNRGGSTQNVSHVRGTLGYIAPEWVSSLPITAKVDVYSYGVVLLELLTGTRVSELVGGTDEVHSMLRKLVRMLSAKLEGEEQSWIDGYLDSKLNRPVNYVQARTLIKLAVSCL",
+        "QIRLTGRVGSGRFGNVSRGDYRGEAVAVKVFNALDEPAFHKETEIFETRMLRHPNVLRYIGSDRVDTGFVTELWLVTEYHPSGSLHDFLLENTVNIETYYNLMRSTASGLAFLHNQIGGSKESNKPAMAHRDIKSKNIMVKNDLTCAIGDLGLSLSKPEDAASDIIANENYKCGTVRYLAPEILNSTMQFTVFESYQCADVYSFSLVMWETLCRCEDGDVLPREAATVIPYIEWTDRDPQDAQMFDVVCTRRLRPTENPLWKDHPEMKHIMEI",
+        "HYKVGRRIGEGSFGVIFEGTNLLNNQQVAIKFEPRRSDAPQLRDEYRTYKLLAGCTGIPNVYYFGQEGLHNVLVIDLLGPSLEDLLDLCGRKFSVKTVAMAAKQMLARVQSIHEKSLVYRDIKPDNFLIGRPNSKNANMIYVVDFGMVKFYRDPVTKQHIPYREKKNLSGTARYMSINTHLGREQSRRDDLEALGHVFMYFLRGSLPWQGLKAATNKQKYERIGEKKQSTPLRELCAGFPEEFYKYMHYARNLAFDATPDYDYLQGLFSKVL"],
+}
+
+# name -> sequences of every parity case; sizes chosen so the CPU oracle finishes in seconds
+CASES = dict(FIXTURES)
+CASES.update({
+    "rnd4x60": random_seqs(4, 60, 1),
+    "fam6x80": family_seqs(6, 80, 2),
+    "rnd7x120": random_seqs(7, 120, 3),
+    "fam3x300": family_seqs(3, 300, 4, 0.3, 0.05),
+    "fam5x60": family_seqs(5, 60, 11, 0.15, 0.03),
+    "fam4x150": family_seqs(4, 150, 12, 0.25, 0.04),
+    "fam7x30": family_seqs(7, 30, 14, 0.2, 0.04),
+    "fam8x20": family_seqs(8, 20, 15, 0.15, 0.03),
+    "fam9x30": family_seqs(9, 30, 5),
+    "fam10x20": family_seqs(10, 20, 6, 0.2, 0.05),
+    "fam14x6": family_seqs(14, 6, 21, 0.2, 0.0),
+    "fam16x5": family_seqs(16, 5, 22, 0.2, 0.0),
+})
+S7 = lambda: random_seqs(7, 500, 12345)   # BASELINE.json configs[3]
+S8 = lambda: random_seqs(8, 1000, 12345)  # BASELINE.json configs[4] (DP part; L=1000 is outside the weight routine's reference domain)
+
+# known answers from the unmodified reference arithmetic (re-derived by tests/golden/make_golden.py)
+KNOWN_OPT = {"test": 52440, "test2": 45037, "PF08184": 24450, "kinase": 421546}
+
+
+def random_parents(seqs, k, seed):
+    """k parents: origin, final, near-border and random interior coordinates with random g / parenti."""
+    rng = np.random.default_rng(seed)
+    n = len(seqs)
+    lens = np.array([len(s) for s in seqs])
+    pos = np.stack([rng.integers(0, lens + 1) for _ in range(k)]).astype(np.uint16)
+    pos[0] = 0
+    if k > 1:
+        pos[1] = lens
+    if k > 2:
+        pos[2] = lens - 1
+    if k > 3:
+        pos[3] = lens - 1
+        pos[3][0] = lens[0]
+    g = rng.integers(0, 100000, k).astype(np.int32)
+    par = rng.integers(1, 1 << n, k).astype(np.int32)
+    return pos, g, par
+
+
+def weighted_sp_score(seqs, w_int, rows):
+    """Re-score an alignment under the reference's cost model (Node.cpp:129-152, 240-243): the g of its path."""
+    from oracle import oracle as O
+    cost = O.cost_table()
+    n = len(seqs)
+    cols = len(rows[0])
+    assert all(len(r) == cols for r in rows)
+    for i in range(n):
+        assert rows[i].replace("-", "") == seqs[i]
+    prev = [1] * n  # initial parenti: all ones (Sequences.cpp:75)
+    total = 0
+    for c in range(cols):
+        mv = [0 if rows[i][c] == "-" else 1 for i in range(n)]
+        assert any(mv)
+        for x in range(n - 1):
+            for y in range(x + 1, n):
+                if mv[x] and mv[y]:
+                    t = int(cost[ord(rows[x][c]), ord(rows[y][c])])
+                elif mv[x] or mv[y]:
+                    s = y if mv[x] else x
+                    t = 30 if prev[s] != mv[s] else 30  # GapOpen == GapExtension (Cost.h:13)
+                else:
+                    t = 30  # GapGap
+                total += t * int(w_int[x][y])
+        prev = mv
+    return total
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    import mpi_pastar_msa_b200 as m
+    if not has_gpu():
+        pytest.skip("no CUDA device")
+    return m

@@ -1,0 +1,60 @@
+"""GPU parity (3)+(4): the batched search reaches the reference's optimal cost, bit-exact, on every terminating input."""
+import numpy as np
+import pytest
+
+from conftest import CASES, KNOWN_OPT, weighted_sp_score
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["test", "test2", "PF08184", "rnd4x60", "fam6x80", "fam3x300", "fam5x60", "fam4x150", "fam7x30", "fam8x20"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("batch", [1, 64, 16384])
+def test_optimal_cost_matches_oracle(gpu_lib, name, batch):
+    seqs = CASES[name]
+    ref = O.Problem(seqs).astar(want_rows=False)
+    assert ref["finished"]
+    if name in KNOWN_OPT:
+        assert ref["g"] == KNOWN_OPT[name]
+    with gpu_lib.PastarGPU(seqs) as G:
+        G.build_pair_tables()
+        r = G.search(table_capacity=1 << 22, batch_target=batch)
+        assert r["finished"] == 1
+        assert r["g"] == ref["g"] and r["f"] == ref["g"], (name, batch, r, ref)
+        # the printed alignment re-scores to g* under the weighted cost model
+        assert weighted_sp_score(seqs, G.w_int, r["rows"]) == r["g"]
+        assert r["align_len"] == len(r["rows"][0])
+        # batch 1 pops one f-layer node at a time: never more expansions than nodes with f <= g*
+        assert r["expansions"] >= 1 and r["generated"] >= r["expansions"]
+
+
+def test_kinase_full(gpu_lib):
+    """BASELINE configs[1]: kinase.fasta full A* MSA on one B200, optimal cost bit-exact vs the reference."""
+    seqs = CASES["kinase"]
+    with gpu_lib.PastarGPU(seqs) as G:
+        G.build_pair_tables()
+        assert int(G.calculate_h(np.zeros((1, 5), dtype=np.uint16))[0]) == 408457  # h(start), SURVEY §4
+        r = G.search(table_capacity=1 << 27, batch_target=16384)
+        assert r["finished"] == 1 and r["g"] == KNOWN_OPT["kinase"] == 421546
+        assert weighted_sp_score(seqs, G.w_int, r["rows"]) == 421546
+
+
+def test_budgeted_run_stops(gpu_lib):
+    from conftest import random_seqs
+    seqs = random_seqs(7, 400, 3)
+    with gpu_lib.PastarGPU(seqs) as G:
+        G.build_pair_tables()
+        r = G.search(table_capacity=1 << 24, batch_target=4096, max_expansions=50000)
+        assert r["finished"] == 0 and r["expansions"] >= 50000
+        assert r["generated"] > r["expansions"] * 60
+
+
+def test_table_capacity_error(gpu_lib):
+    seqs = CASES["fam6x80"]
+    with gpu_lib.PastarGPU(seqs) as G:
+        G.build_pair_tables()
+        with pytest.raises(gpu_lib.PastarError) as e:
+            G.search(table_capacity=1024, batch_target=4096)
+        assert e.value.code == 4  # PG_ERR_CAPACITY, not a wrong answer
