@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — node expansions/s of the batched PA-Star search on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[3], synthetic N=7 x length 500 random protein (seed 12345),
+PAM250 costs, Altschul weights, budgeted A* search (random sets never terminate: SURVEY §7).
+A step = one search round of the hot path: pop `batch` frontier nodes -> expand all 2^N-1 successors of each
+(g via weighted SP, h via pairwise tables, owner) -> closed/open-table dedupe -> push survivors (+ exchange for N>1).
+value  = expansions in the K timed steps / device time (state resident in HBM), whole job over all ranks.
+e2e    = same metric through the C ABI from HOST buffers: context create (H2D of sequences, cost, weights), pairwise
+         tables, search to the same expansion budget, result D2H; wall clock around the calls.
+roofline = the fused expand+dedupe kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+cpu_baseline / --impl reference = the reference's own getNeigh / PairAlign / weights (oracle/_ref, compiled from
+         the unmodified sources) under the restated T-thread hash-partitioned driver, on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+AA = "ACDEFGHIKLMNPQRSTVWY"
+METRIC, UNIT = "node_expansions_per_sec", "expansions/s"
+N_SEQ, LENGTH, SEED = 7, 500, 12345
+WORKLOAD = "synthetic N=7 x L=500 random protein (seed 12345), PAM250 costs, Altschul weights, budgeted A* search"
+CPU_STEP_POPS = 1000  # the reference arm's step: a bounded sample of the same search
+
+
+def s7_seqs():
+    import random
+    r = random.Random(SEED)
+    return ["".join(r.choice(AA) for _ in range(LENGTH)) for _ in range(N_SEQ)]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons DURING the timed region (NVML, ~5 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        for k, bit in names.items():
+            if r & bit:
+                self.reasons.add(k)
+
+    def run(self):
+        if not self.nv:
+            return
+        while not self.stop_flag:
+            try:
+                self.sample()
+            except Exception:
+                break
+            time.sleep(0.005)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_run(threads, steps, warmup, want_sample=True):
+    """The reference CPU path on S7: oracle/_ref (reference arithmetic + restated T-thread driver), else the C port."""
+    from oracle import refio
+    seqs = s7_seqs()
+    budget = (steps + warmup) * CPU_STEP_POPS
+    if refio.available():
+        r = refio.pastar(seqs, threads, budget, "FZORDER", 12, timeout=1800, warm_pops=max(1, warmup * CPU_STEP_POPS))
+        secs, exps = r["timed_seconds"], r["timed_expansions"]
+        kind, cores = "reference", threads
+        what = ("oracle/_ref: reference Node::getNeigh/PairAlign/weights under the restated hash-partitioned PA-Star driver "
+                "(PAStar.cpp:319-547; Boost/MPI absent), %d threads x 1 rank" % threads)
+    else:
+        from oracle import oracle as O
+        P = O.Problem(seqs)
+        P.astar(budget=max(1, warmup * CPU_STEP_POPS), want_rows=False)
+        t0 = time.time()
+        r = P.astar(budget=budget, want_rows=False)
+        secs, exps = time.time() - t0, r["expansions"]
+        kind, cores = "port", 1
+        what = "oracle/pastar_oracle.c serial A* (AStar.cpp:53-104 restated), 1 thread"
+    return {"value": exps / secs if secs > 0 else 0.0, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%s; %d dequeues timed after %d warm-up dequeues of the S7 search" % (what, steps * CPU_STEP_POPS, warmup * CPU_STEP_POPS),
+            "seconds": secs, "expansions": exps}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    t0 = time.time()
+    b = cpu_reference_run(threads, steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * b["seconds"] / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "%d dequeues of the CPU search" % CPU_STEP_POPS, "threads": threads, "ranks": 1,
+                       "nproc": os.cpu_count()},
+            "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world):
+    import torch
+    import mpi_pastar_msa_b200 as m
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    seqs = s7_seqs()
+    batch, cap = args.batch, args.table_capacity
+    K, W = max(1, args.steps), max(3, args.warmup)
+    stream = torch.cuda.current_stream()
+
+    G = m.PastarGPU(seqs, device=local)
+    G.set_stream(stream.cuda_stream)
+    dp_ms = min(G.build_pair_tables() for _ in range(3))
+    cells = sum((len(a) + 1) * (len(b) + 1) for i, a in enumerate(seqs) for b in seqs[i + 1:])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_step = 2  # select + fused expand
+    extra = {}
+    if world == 1:
+        G.search_begin(1, 0, cap, batch)
+        # ---- ramp-up (untimed): grow the frontier from the start node until rounds pop full batches
+        ramp = 0
+        while True:
+            before = G.search_status()[2]["pops"]
+            G.search_rounds(8)
+            ramp += 8
+            if G.search_status()[2]["pops"] - before >= 8 * batch or ramp > 4000:
+                break
+        G.search_rounds(W)
+        c0 = G.search_status()[2]
+        G.search_profile(True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        G.search_rounds(K)
+        e1.record(stream)
+        barrier()
+        sampler.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        c1 = G.search_status()[2]
+        G.search_profile(False)
+        d = {k: c1[k] - c0[k] for k in ("expansions", "generated", "probed", "pushed", "pops")}
+        expand_ms, select_ms = c1["expand_ms"] - c0["expand_ms"], c1["select_ms"] - c0["select_ms"]
+        total_exp = d["expansions"]
+        max_ms = ms
+        G.search_end()
+    else:
+        from mpi_pastar_msa_b200.dist import CudaEngine, PartitionedSearch
+        G.configure_hash("FZORDER", 12)
+        eng = CudaEngine(G, world, rank, cap, batch)
+        drv = PartitionedSearch(eng, dist, seqs, lambda pos: int(G.owner(np.array(pos, dtype=np.uint16), world)[0]))
+        launches_per_step = 4  # select + fused expand + insert + status select
+        ramp = 0
+        while True:
+            _, _, tot0 = drv.step()
+            ramp += 1
+            if ramp >= 8:
+                _, _, tot1 = drv.step()
+                ramp += 1
+                if tot1[2] - tot0[2] >= world * batch or ramp > 4000:
+                    break
+        for _ in range(W):
+            drv.step()
+        _, _, tot0 = drv.step()
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sent0 = drv.bytes_sent
+        for _ in range(K):
+            _, _, tot1 = drv.step()
+        e1.record(stream)
+        barrier()
+        sampler.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_ms = float(t.item())
+        total_exp = tot1[0] - tot0[0]
+        d = {"expansions": total_exp, "generated": tot1[1] - tot0[1], "pops": tot1[2] - tot0[2]}
+        extra["nvlink_bytes_per_step_per_gpu"] = (drv.bytes_sent - sent0) / K
+        expand_ms = select_ms = None
+        eng.end()
+
+    value = total_exp / (max_ms * 1e-3)
+    clocks = sampler.result()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "table_slots_per_gpu": cap, "parallelism": "hash-partition x%d" % world,
+                       "ramp_up_rounds_untimed": ramp,
+                       "l2": "inputs larger than L2: %.1f GiB hash table per GPU, ~%d MB of distinct sectors touched per step"
+                             % (cap * 16 / 2**30, batch * 127 * 32 // 10**6)},
+            "clocks": clocks, "gpu_launches": launches_per_step * K,
+            "successors_per_sec": d["generated"] / (max_ms * 1e-3)}
+
+    if world == 1:
+        hbm, how = measured_peaks()
+        P, S, n = G.npairs, G.S, G.n
+        # algorithmic bytes of the fused kernel: per expansion the open-list slot (4) + table entry (16)
+        # + residues (N) + 4 cells per pair (16 P); per probed successor one 32 B table sector; per pushed successor
+        # the sector written back (32) + its open-list slot (4).
+        alg = d["expansions"] * (20 + n + 16 * P) + d["probed"] * 32 + d["pushed"] * 36
+        achieved = alg / (expand_ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "search_expand_kernel<7,1>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                            "frac": achieved / hbm, "traffic": None, "peak_source": how, "launches": K,
+                            "avg_launch_us": 1e3 * expand_ms / K, "algorithmic_bytes_per_launch": alg / K,
+                            "share_of_step": expand_ms / ms, "select_kernel_share": select_ms / ms}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                line["roofline"]["traffic"] = json.load(open(tr)).get("search_expand_dram_bytes_per_launch")
+            except Exception:
+                pass
+        # ---- pairwise DP and stand-alone expansion kernel (the other two headline kernels)
+        st = stream.cuda_stream
+        Kx = 100000
+        rng = np.random.default_rng(1)
+        pos = np.stack([rng.integers(0, LENGTH, Kx) for _ in range(n)], axis=1).astype(np.uint16)
+        nodes = G.make_nodes(pos, rng.integers(0, 100000, Kx), rng.integers(1, 1 << n, Kx))
+        d_par = torch.from_numpy(nodes.view(np.uint8).reshape(Kx, -1)).cuda()
+        sst = m.succ_dtype(n).itemsize
+        d_out = torch.empty(Kx * S * sst, dtype=torch.uint8, device="cuda")
+        d_cnt = torch.empty(Kx, dtype=torch.int32, device="cuda")
+        for _ in range(3):
+            G.expand_batch_dev(d_par.data_ptr(), Kx, 8, d_out.data_ptr(), d_cnt.data_ptr(), st)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(10):
+            G.expand_batch_dev(d_par.data_ptr(), Kx, 8, d_out.data_ptr(), d_cnt.data_ptr(), st)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        xms = a0.elapsed_time(a1) / 10
+        bexp = m.node_dtype(n).itemsize + n + 16 * P + S * sst  # 4435 B at N=7
+        extra["expand_only"] = {"kernel": "expand_batch_kernel<7>", "expansions_per_sec": Kx / (xms * 1e-3), "successors_per_sec": Kx * S / (xms * 1e-3),
+                                "bytes_per_expansion": bexp, "achieved_gbs": Kx * bexp / (xms * 1e-3) / 1e9,
+                                "frac_of_hbm": Kx * bexp / (xms * 1e-3) / 1e9 / hbm, "output_mb": Kx * S * sst / 1e6}
+        extra["pair_dp"] = {"kernel": "pair_dp_kernel", "cells": cells, "ms": dp_ms, "gcups": cells / (dp_ms * 1e-3) / 1e9}
+        del d_out
+
+        # ---- e2e: host buffers -> C ABI -> result, same expansion budget as ramp-up + warm-up + timed region
+        budget = c1["expansions"]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        G2 = m.PastarGPU(seqs, device=local)          # host weights + H2D of residues / cost table / weights
+        G2.build_pair_tables()
+        r = G2.search(table_capacity=cap, batch_target=batch, max_expansions=budget, want_rows=False)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        G2.close()
+        h2d = sum(((len(s) + 16) & ~15) for s in seqs) + 8100 * 4 + 2 * n + 16
+        d2h = (r["rounds"] // 8 + 2) * 128 + 16
+        line["e2e"] = {"value": r["expansions"] / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(1, r["rounds"]),
+                       "d2h_bytes_per_step": d2h / max(1, r["rounds"]), "expansions": r["expansions"], "rounds": r["rounds"],
+                       "wall_s": wall, "includes": "host Altschul weights, context create, pairwise DP, search from the start node, result read-back"}
+        # ---- CPU baseline beside it (bounded sample)
+        try:
+            threads = os.cpu_count() or 1
+            b = cpu_reference_run(threads, 20, 5)
+            line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # never lose the GPU numbers to a CPU-side hiccup
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+    else:
+        # end to end at N GPUs: wall clock over the same timed rounds including NCCL exchange and per-round host reads
+        line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 8 * world, "d2h_bytes_per_step": 8 * world + 128,
+                       "note": "step-wise driver: every round already returns counts/status to the host"}
+    line["extra"] = extra
+    G.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=131072)
+    ap.add_argument("--table-capacity", type=int, default=1 << 30)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,9 @@ int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens, const int
 void pg_ctx_destroy(pg_ctx *ctx);
 const char *pg_last_error(const pg_ctx *ctx);
 int pg_abi_version(void);
+/* Run every later launch of this context on the caller's stream (cudaStream_t as void*; NULL = the
+ * context's own stream), e.g. torch's current stream so that the caller's CUDA events bracket the work. */
+int pg_ctx_set_stream(pg_ctx *ctx, void *stream);
 
 /* ------------------------------------------------------------------ (1) pairwise DP heuristic */
 
@@ -132,8 +135,13 @@ typedef struct {
     int64_t reopen;         /* PAStar.cpp:231,347                                                */
     int64_t open_size, closed_size;
     int64_t rounds;
+    int64_t probed;         /* successors looked up in the closed/open table (generated - pruned) */
+    int64_t pushed;         /* successors that were new or strictly better: pushed to the open list */
+    int64_t inserted;       /* distinct coordinates in the table                                  */
     double seconds;         /* phase-2 wall time                                                 */
-    double kernel_ms;       /* CUDA-event time of the expansion kernels                          */
+    double kernel_ms;       /* CUDA-event time from the first to the last round of the search     */
+    double expand_ms;       /* sum of the fused expand kernel's launch durations (profiling on)  */
+    double select_ms;       /* sum of the select kernel's launch durations (profiling on)        */
 } pg_result;
 
 /* Replaces PAStar<N>::pa_star (pastar/PAStar.cpp:626-673) on ONE GPU
@@ -152,6 +160,10 @@ int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg);
  * owned by this partition are deduped and pushed, the others are appended to
  * per-destination outboxes as pg_xrec records. */
 int pg_search_round(pg_ctx *ctx, int32_t f_limit);
+/* `rounds` rounds back to back with one host synchronisation at the end (single partition only). */
+int pg_search_rounds(pg_ctx *ctx, int32_t rounds, int32_t f_limit);
+/* Per-launch CUDA-event timing of the select and expand kernels (off by default: two event records per launch). */
+int pg_search_profile(pg_ctx *ctx, int enable);
 /* Device pointer + record count of the outbox for partition dst (valid until the next round). */
 int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count);
 /* Dedupe + push records received from other partitions (device pointer). */

@@ -36,7 +36,9 @@ class SearchConfig(C.Structure):
 class Result(C.Structure):
     _fields_ = [("finished", C.c_int32), ("g", C.c_int32), ("f", C.c_int32), ("align_len", C.c_int32), ("pops", C.c_int64),
                 ("expansions", C.c_int64), ("generated", C.c_int64), ("reopen", C.c_int64), ("open_size", C.c_int64),
-                ("closed_size", C.c_int64), ("rounds", C.c_int64), ("seconds", C.c_double), ("kernel_ms", C.c_double)]
+                ("closed_size", C.c_int64), ("rounds", C.c_int64), ("probed", C.c_int64), ("pushed", C.c_int64),
+                ("inserted", C.c_int64), ("seconds", C.c_double), ("kernel_ms", C.c_double), ("expand_ms", C.c_double),
+                ("select_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -66,6 +68,9 @@ def load_library():
         "pg_host_weights": ([i32, C.POINTER(C.c_char_p), C.POINTER(i32), vp], i32),
         "pg_ctx_create": ([i32, C.POINTER(C.c_char_p), C.POINTER(i32), vp, i32, i32, i32, vp, i32, C.POINTER(vp)], i32),
         "pg_ctx_destroy": ([vp], None),
+        "pg_ctx_set_stream": ([vp, vp], i32),
+        "pg_search_rounds": ([vp, C.c_int32, C.c_int32], i32),
+        "pg_search_profile": ([vp, i32], i32),
         "pg_build_pair_tables": ([vp, C.POINTER(C.c_float)], i32),
         "pg_pair_table_shape": ([vp, i32, C.POINTER(i32), C.POINTER(i32)], i32),
         "pg_copy_pair_table": ([vp, i32, vp], i32),
@@ -92,7 +97,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
+EXPORTS = ["pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
            "pg_search_outbox", "pg_search_insert_dev", "pg_search_status", "pg_search_lookup", "pg_search_end",
@@ -285,6 +290,16 @@ class PastarGPU:
 
     def search_round(self, f_limit=2**31 - 1):
         self._ck(self.L.pg_search_round(self.h, f_limit))
+
+    def search_rounds(self, rounds, f_limit=2**31 - 1):
+        self._ck(self.L.pg_search_rounds(self.h, rounds, f_limit))
+
+    def search_profile(self, enable=True):
+        self._ck(self.L.pg_search_profile(self.h, 1 if enable else 0))
+
+    def set_stream(self, stream):
+        """cudaStream_t handle (int) the context launches on; 0/None = its own stream."""
+        self._ck(self.L.pg_ctx_set_stream(self.h, stream or None))
 
     def search_outbox(self, dst):
         p, n = C.c_void_p(), C.c_int64()

@@ -73,7 +73,8 @@ extern "C" int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens
     dp.hash_type = PG_HASH_FZORDER; // CoordHash.cpp:17-18 defaults
     dp.hash_shift = 12;
 
-    PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
     PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
 
     // residues: one arena, each sequence padded with a trailing 0 (Node.cpp:225 reads seq[len])
@@ -153,9 +154,16 @@ extern "C" void pg_ctx_destroy(pg_ctx *ctx)
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     for (int i = 0; i < 2; i++)
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
+}
+
+extern "C" int pg_ctx_set_stream(pg_ctx *ctx, void *stream)
+{
+    if (!ctx) return PG_ERR_ARG;
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return PG_OK;
 }
 
 extern "C" int pg_build_pair_tables(pg_ctx *ctx, float *kernel_ms)

@@ -66,7 +66,8 @@ struct pg_ctx {
     size_t table_cells = 0;
     bool tables_built = false;
     int sm_count = PG_SM_COUNT_B200;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream all launches go to (own_stream unless pg_ctx_set_stream)
+    cudaStream_t own_stream = nullptr;
     cudaStream_t stream2 = nullptr;
     // staging for the host-pointer entry points
     void *d_stage[2] = {nullptr, nullptr};

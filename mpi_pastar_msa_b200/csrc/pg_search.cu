@@ -30,6 +30,7 @@
 #include <chrono>
 #include <climits>
 #include <cstring>
+#include <vector>
 
 #include "pg_expand_core.cuh"
 
@@ -79,6 +80,11 @@ struct SearchState {
     uint64_t outbox_cap = 0; // records per destination
     int xrec = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-launch timing: event triples (before select, between, after expand), harvested at every sync
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    double expand_ms = 0, select_ms = 0;
     double kernel_ms = 0;
     int64_t rounds = 0;
     bool active = false;
@@ -939,14 +945,45 @@ int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st)
     return pg_fail(ctx, PG_ERR_ARG, "unsupported number of sequences");
 }
 
+int prof_event(pg_ctx *ctx)
+{
+    SearchState *s = ctx->search;
+    if (s->prof_used == s->prof_ev.size()) {
+        cudaEvent_t e;
+        PG_CUDA(ctx, cudaEventCreate(&e));
+        s->prof_ev.push_back(e);
+    }
+    PG_CUDA(ctx, cudaEventRecord(s->prof_ev[s->prof_used++], ctx->stream));
+    return PG_OK;
+}
+
+int prof_harvest(pg_ctx *ctx) // after a stream synchronise
+{
+    SearchState *s = ctx->search;
+    for (size_t i = 0; i + 2 < s->prof_used; i += 3) {
+        float a = 0, b = 0;
+        PG_CUDA(ctx, cudaEventElapsedTime(&a, s->prof_ev[i], s->prof_ev[i + 1]));
+        PG_CUDA(ctx, cudaEventElapsedTime(&b, s->prof_ev[i + 1], s->prof_ev[i + 2]));
+        s->select_ms += a;
+        s->expand_ms += b;
+    }
+    s->prof_used = 0;
+    return PG_OK;
+}
+
 int launch_round(pg_ctx *ctx, int f_limit)
 {
     SearchState *s = ctx->search;
+    int rc;
+    if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     select_kernel<<<1, SELECT_THREADS, 0, ctx->stream>>>(dev_search(ctx), (long long)s->batch_target, f_limit);
     PG_CUDA(ctx, cudaGetLastError());
-    int rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
+    if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
+    rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
+    if (rc != PG_OK) return rc;
+    if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     s->rounds++;
-    return rc;
+    return PG_OK;
 }
 
 int sync_ctrl(pg_ctx *ctx)
@@ -954,6 +991,10 @@ int sync_ctrl(pg_ctx *ctx)
     SearchState *s = ctx->search;
     PG_CUDA(ctx, cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(SearchCtrl), cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (s->profile) {
+        int rc = prof_harvest(ctx);
+        if (rc != PG_OK) return rc;
+    }
     switch (s->h_ctrl->error) {
     case 0:
         return PG_OK;
@@ -976,7 +1017,12 @@ void fill_counters(const SearchState *s, pg_result *r)
     r->generated = (int64_t)c->generated;
     r->reopen = (int64_t)c->reopen;
     r->rounds = s->rounds;
+    r->probed = (int64_t)(c->generated - c->pruned);
+    r->pushed = (int64_t)c->pushed;
+    r->inserted = (int64_t)c->inserted;
     r->kernel_ms = s->kernel_ms;
+    r->expand_ms = s->expand_ms;
+    r->select_ms = s->select_ms;
 }
 
 } // namespace
@@ -999,6 +1045,7 @@ void pg_search_free(pg_ctx *ctx)
     if (s->h_outbox_count) cudaFreeHost(s->h_outbox_count);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     delete s;
     ctx->search = nullptr;
 }
@@ -1135,6 +1182,25 @@ extern "C" int pg_search_round(pg_ctx *ctx, int32_t f_limit)
     if (s->cfg.n_parts > 1)
         PG_CUDA(ctx, cudaMemcpyAsync(s->h_outbox_count, s->d_outbox_count, 8 * 64, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_ctrl(ctx);
+}
+
+extern "C" int pg_search_rounds(pg_ctx *ctx, int32_t rounds, int32_t f_limit)
+{
+    if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
+    if (ctx->search->cfg.n_parts != 1) return pg_fail(ctx, PG_ERR_ARG, "pg_search_rounds is for a single partition");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < rounds; r++) {
+        int rc = launch_round(ctx, f_limit);
+        if (rc != PG_OK) return rc;
+    }
+    return sync_ctrl(ctx);
+}
+
+extern "C" int pg_search_profile(pg_ctx *ctx, int enable)
+{
+    if (!ctx || !ctx->search) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
+    ctx->search->profile = enable != 0;
+    return PG_OK;
 }
 
 extern "C" int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count)

@@ -1,0 +1,155 @@
+"""Hash-partitioned multi-GPU PA-Star: one process per GPU (torchrun), one partition per GPU.
+
+Replaces the reference's distribution layer for the successor path:
+  worker_inner reconciliation      pastar/PAStar.cpp:366-396         -> per-destination outboxes filled on the device
+  sender / receiver / decoder      pastar/pastar_functions/PAStarSender.cpp:11-112, PAStarReceiver.cpp:11-107,
+                                   PAStarMessageProcesser.cpp:12-78  -> one NCCL all-to-all of fixed-width records
+  check_stop's two allreduces      pastar/PAStar.cpp:502-519          -> one allreduce(min) of {min open f, best goal g}
+  distributed backtrace            pastar_functions/PAStarDistributedBacktrace.cpp:18-214 -> owner lookups + allreduce
+
+Per round, on every rank:   expand own frontier  ->  all-to-all(successors by owner)  ->  dedupe + push  ->  allreduce(min).
+There is nothing in flight between rounds, so the reference's optimality-preserving stop (accept the goal only when
+no open node anywhere has f < g_goal and no message is in flight) is exactly `min over ranks of min_open_f >= min over
+ranks of best_goal_g`.
+
+The engine is the CUDA context (PastarGPU).  The driver only moves bytes; torch.distributed is plumbing (NCCL on GPUs,
+gloo in the CPU tests where a test-only engine stands in for the kernels).
+"""
+import numpy as np
+
+INT_MAX = 2**31 - 1
+
+
+class CudaEngine:
+    """Adapter: PastarGPU step-wise search -> the byte-tensor interface the driver speaks."""
+
+    def __init__(self, gpu, n_parts, part, table_capacity=0, batch_target=0):
+        import torch
+        self.torch = torch
+        self.g = gpu
+        self.n_parts, self.part = n_parts, part
+        gpu.search_begin(n_parts, part, table_capacity, batch_target)
+        self.xrec = gpu.xrec_stride()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def _wrap(self, ptr, nbytes):
+        class _Mem:  # zero-copy view of library-owned device memory
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        return self.torch.as_tensor(_Mem(), device=self.device)
+
+    def round(self, f_limit):
+        """Expand this partition's frontier; returns the per-destination outboxes as uint8 tensors."""
+        self.g.search_round(f_limit)
+        out = []
+        for dst in range(self.n_parts):
+            if dst == self.part:
+                out.append(self.torch.empty(0, dtype=self.torch.uint8, device=self.device))
+                continue
+            ptr, n = self.g.search_outbox(dst)
+            out.append(self._wrap(ptr, n * self.xrec) if n else self.torch.empty(0, dtype=self.torch.uint8, device=self.device))
+        return out
+
+    def insert(self, buf):
+        if buf.numel():
+            self.g.search_insert_dev(buf.data_ptr(), buf.numel() // self.xrec)
+
+    def status(self):
+        return self.g.search_status()
+
+    def lookup(self, pos):
+        return self.g.search_lookup(pos)
+
+    def empty(self, nbytes):
+        return self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
+
+    def end(self):
+        self.g.search_end()
+
+
+class PartitionedSearch:
+    """The per-rank loop.  `dist` is torch.distributed (initialised by the caller), engine as above."""
+
+    def __init__(self, engine, dist, seqs, owner_fn, max_expansions=0):
+        import torch
+        self.torch, self.e, self.dist = torch, engine, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.seqs = seqs
+        self.owner_fn = owner_fn  # coord -> owning partition (Coord::get_id(world))
+        self.max_expansions = max_expansions
+        self.rounds = 0
+        self.bytes_sent = 0
+
+    def _dev(self):
+        return getattr(self.e, "device", self.torch.device("cpu"))
+
+    def exchange(self, outboxes):
+        """All-to-all of variable-length record buffers: counts first, then the payload."""
+        t, dist = self.torch, self.dist
+        send_n = t.tensor([b.numel() for b in outboxes], dtype=t.int64, device=self._dev())
+        recv_n = t.empty_like(send_n)
+        dist.all_to_all_single(recv_n, send_n)
+        recv_n = recv_n.tolist()
+        send_l = send_n.tolist()
+        inbox = self.e.empty(int(sum(recv_n)))
+        # all_to_all_single with split sizes (the list form is not implemented by gloo); the outboxes live in one
+        # allocation with gaps, so they are compacted into one send buffer first
+        payload = t.cat(outboxes) if sum(send_l) else self.e.empty(0)
+        dist.all_to_all_single(inbox, payload, output_split_sizes=recv_n, input_split_sizes=send_l)
+        self.bytes_sent += int(sum(send_l))
+        return inbox
+
+    def step(self, f_limit=INT_MAX):
+        """One round; returns (global min open f, global best goal g, global expansions)."""
+        t, dist = self.torch, self.dist
+        outboxes = self.e.round(f_limit)
+        self.e.insert(self.exchange(outboxes))
+        mn, best, cnt = self.e.status()
+        red = t.tensor([mn, best], dtype=t.int64, device=self._dev())
+        dist.all_reduce(red, op=dist.ReduceOp.MIN)
+        tot = t.tensor([cnt["expansions"], cnt["generated"], cnt["pops"]], dtype=t.int64, device=self._dev())
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        self.rounds += 1
+        return int(red[0]), int(red[1]), [int(x) for x in tot]
+
+    def run(self):
+        """Search to the optimality-preserving stop (or the expansion budget).  Returns a dict on every rank."""
+        best = INT_MAX
+        while True:
+            mn, best, tot = self.step(best)
+            if mn >= best or mn == INT_MAX:  # every open node everywhere has f >= g_goal; nothing in flight
+                finished = best != INT_MAX
+                break
+            if self.max_expansions and tot[0] >= self.max_expansions:
+                finished = False
+                break
+        res = {"finished": int(finished), "g": best if finished else -1, "expansions": tot[0], "generated": tot[1],
+               "pops": tot[2], "rounds": self.rounds}
+        if finished:
+            res["rows"] = self.backtrace()
+        return res
+
+    def backtrace(self):
+        """Walk parenti from the final coordinate; the owner of each coordinate answers (one allreduce per column)."""
+        t, dist = self.torch, self.dist
+        n = len(self.seqs)
+        pos = [len(s) for s in self.seqs]
+        cols = []
+        while any(pos):
+            hit = self.e.lookup(np.array(pos, dtype=np.uint16)) if self.owner_fn(pos) == self.rank else None
+            v = t.tensor([1, hit[0], hit[1]] if hit else [0, -1, -1], dtype=t.int64, device=self._dev())
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            if int(v[0]) != 1:
+                raise RuntimeError("backtrace lost the parent chain at %s" % (pos,))
+            mask = int(v[2])
+            cols.append(mask)
+            pos = [p - ((mask >> i) & 1) for i, p in enumerate(pos)]
+        rows = [[] for _ in range(n)]
+        at = [0] * n
+        for mask in reversed(cols):
+            for i in range(n):
+                if (mask >> i) & 1:
+                    rows[i].append(self.seqs[i][at[i]])
+                    at[i] += 1
+                else:
+                    rows[i].append("-")
+        return ["".join(r) for r in rows]

@@ -245,6 +245,9 @@ struct SearchStats {
     long long closed_size = 0;
     double seconds = 0;
     int finished = 0;
+    // measured after the first `warm_pops` dequeues (bench.py --impl reference: untimed warm-up, then K steps)
+    double timed_seconds = 0;
+    long long timed_expansions = 0;
 };
 
 // Walk parenti from the goal (backtrace.cpp:44-69) and emit the aligned rows.
@@ -321,8 +324,8 @@ template <int N>
 class PAStarStd
 {
   public:
-    PAStarStd(int threads, long long budget)
-        : T(threads), budget(budget), open(threads), closed(threads), inbox(threads), inbox_mutex(threads),
+    PAStarStd(int threads, long long budget, long long warm_pops = 0)
+        : T(threads), budget(budget), warm_pops(warm_pops), open(threads), closed(threads), inbox(threads), inbox_mutex(threads),
           inbox_cv(threads), pops(threads, 0), expansions(threads, 0), generated(threads, 0), reopen(threads, 0)
     {
         end_cond = false;
@@ -331,6 +334,9 @@ class PAStarStd
         final_node.set_max();
         final_node_count = 0;
         total_pops = 0;
+        total_expansions = 0;
+        warm_time = 0;
+        warm_expansions = 0;
         budget_hit = false;
         // PAStar.cpp:153: the start node goes to OpenList[0] whatever its owner
         open[0].conditional_enqueue(Sequences::get_initial_node<N>());
@@ -344,7 +350,8 @@ class PAStarStd
         std::vector<std::thread> th;
         for (int i = 0; i < T; i++) th.push_back(std::thread(&PAStarStd::worker, this, i, coord_final));
         for (size_t i = 0; i < th.size(); i++) th[i].join();
-        st.seconds = now_s() - t0;
+        const double t1 = now_s();
+        st.seconds = t1 - t0;
         for (int i = 0; i < T; i++) {
             st.pops += pops[i];
             st.expansions += expansions[i];
@@ -353,6 +360,8 @@ class PAStarStd
             st.open_size += (long long)open[i].size();
             st.closed_size += (long long)closed[i].size();
         }
+        st.timed_seconds = t1 - (warm_pops > 0 && warm_time > 0 ? warm_time : t0);
+        st.timed_expansions = st.expansions - (warm_pops > 0 && warm_time > 0 ? (long long)warm_expansions : 0);
         if (!budget_hit) {
             st.finished = 1;
             st.g_final = final_node.get_g();
@@ -364,7 +373,9 @@ class PAStarStd
 
   private:
     int T;
-    long long budget;
+    long long budget, warm_pops;
+    double warm_time;
+    std::atomic<long long> total_expansions, warm_expansions;
     std::vector<OpenListStd<N> > open;
     std::vector<std::map<Coord<N>, Node<N> > > closed;
     std::vector<std::vector<Node<N> > > inbox;
@@ -477,7 +488,10 @@ class PAStarStd
                 continue;
             }
             pops[tid] += 1;
-            total_pops++;
+            if (++total_pops == warm_pops) {
+                warm_expansions = (long long)total_expansions;
+                warm_time = now_s();
+            }
             if ((c_search = closed[tid].find(current.pos)) != closed[tid].end()) {
                 if (current.get_g() >= c_search->second.get_g()) continue;
                 reopen[tid] += 1;
@@ -488,6 +502,7 @@ class PAStarStd
                 continue;
             }
             expansions[tid] += 1;
+            total_expansions++;
             current.getNeigh(neigh.data(), T);
             for (int i = 0; i < T; i++) {
                 generated[tid] += (long long)neigh[i].size();
@@ -516,9 +531,9 @@ void print_stats(const char *what, int n, int threads, const SearchStats &st, co
 {
     printf("{\"cmd\": \"%s\", \"n_seq\": %d, \"threads\": %d, \"finished\": %d, \"g\": %d, \"f\": %d, "
            "\"pops\": %lld, \"expansions\": %lld, \"generated\": %lld, \"reopen\": %lld, "
-           "\"open\": %lld, \"closed\": %lld, \"seconds\": %.6f",
+           "\"open\": %lld, \"closed\": %lld, \"seconds\": %.6f, \"timed_seconds\": %.6f, \"timed_expansions\": %lld",
            what, n, threads, st.finished, st.g_final, st.f_final, st.pops, st.expansions, st.generated, st.reopen,
-           st.open_size, st.closed_size, st.seconds);
+           st.open_size, st.closed_size, st.seconds, st.timed_seconds, st.timed_expansions);
     if (!rows.empty()) {
         printf(", \"rows\": [");
         for (size_t i = 0; i < rows.size(); i++) printf("%s\"%s\"", i ? ", " : "", rows[i].c_str());
@@ -528,7 +543,7 @@ void print_stats(const char *what, int n, int threads, const SearchStats &st, co
 }
 
 template <int N>
-int search_run(const std::string &cmd, int threads, long long budget, hashType ht, int shift)
+int search_run(const std::string &cmd, int threads, long long budget, hashType ht, int shift, long long warm)
 {
     std::vector<std::string> rows;
     SearchStats st;
@@ -536,7 +551,7 @@ int search_run(const std::string &cmd, int threads, long long budget, hashType h
         st = astar_run<N>(budget, &rows);
     } else {
         Coord<N>::configure_hash(ht, shift);
-        PAStarStd<N> p(threads, budget);
+        PAStarStd<N> p(threads, budget, warm);
         st = p.run(&rows);
     }
     print_stats(cmd.c_str(), N, threads, st, rows);
@@ -599,7 +614,7 @@ int usage()
                  "       pastar_ref neigh <fasta> <parents.bin> <out.bin> <vec_size> <HASH> <shift>\n"
                  "       pastar_ref owner <fasta> <coords.bin> <out.bin> <vec_size> <HASH> <shift>\n"
                  "       pastar_ref astar <fasta> [budget]\n"
-                 "       pastar_ref pastar <fasta> <threads> [budget] [HASH] [shift]\n"
+                 "       pastar_ref pastar <fasta> <threads> [budget] [HASH] [shift] [warm_pops]\n"
                  "       pastar_ref micro <fasta> [seconds]\n";
     return 2;
 }
@@ -646,6 +661,7 @@ int main(int argc, char **argv)
         long long budget = 0;
         hashType ht = HashFZorder;
         int shift = 12;
+        long long warm = 0;
         if (cmd == "astar") {
             if (argc > 3) budget = atoll(argv[3]);
         } else {
@@ -654,8 +670,9 @@ int main(int argc, char **argv)
             if (argc > 4) budget = atoll(argv[4]);
             if (argc > 5) ht = parse_hash(argv[5]);
             if (argc > 6) shift = atoi(argv[6]);
+            if (argc > 7) warm = atoll(argv[7]);
         }
-#define CALL(X) search_run<X>(cmd, threads, budget, ht, shift)
+#define CALL(X) search_run<X>(cmd, threads, budget, ht, shift, warm)
         switch (n) { MAX_NUM_SEQ_HELPER(DISPATCH) }
 #undef CALL
     } else if (cmd == "micro") {

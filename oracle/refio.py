@@ -123,8 +123,8 @@ def astar(seqs_or_path, budget=0, timeout=3600):
     return _search(["astar"], seqs_or_path, [budget], timeout)
 
 
-def pastar(seqs_or_path, threads, budget=0, hash_type="FZORDER", shift=12, timeout=3600):
-    return _search(["pastar"], seqs_or_path, [threads, budget, hash_type, shift], timeout)
+def pastar(seqs_or_path, threads, budget=0, hash_type="FZORDER", shift=12, timeout=3600, warm_pops=0):
+    return _search(["pastar"], seqs_or_path, [threads, budget, hash_type, shift, warm_pops], timeout)
 
 
 def micro(seqs_or_path, seconds=2.0, timeout=600):
