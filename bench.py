@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=131072)
+    ap.add_argument("--batch", type=int, default=1 << 20, help="open-list entries popped per round and GPU")
     ap.add_argument("--table-capacity", type=int, default=1 << 30)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

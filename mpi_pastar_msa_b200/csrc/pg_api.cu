@@ -59,6 +59,8 @@ extern "C" int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens
         return PG_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    // the closed/open table is probed at random: fetch single 32 B sectors from HBM, not whole lines
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     ctx->n = n_seq;
     ctx->npairs = n_seq * (n_seq - 1) / 2;
     *out = ctx; // from here on errors leave a context whose message can be read; caller destroys it

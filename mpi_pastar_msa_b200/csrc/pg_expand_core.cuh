@@ -38,8 +38,8 @@ struct ExpCfg {
     static constexpr int S = (1 << N) - 1;
     static constexpr int NODE_WORDS = (((2 * N + 3) & ~3) + 12) / 4;
     static constexpr int POS_WORDS = ((2 * N + 3) & ~3) / 4;
-    // ints of shared memory per parent group: LUTg, LUTh, HHg, HHh, pos
-    static constexpr int GROUP_INTS = 8 * P + 2 * H + PG_MAX_SEQ;
+    // ints of shared memory per parent group: LUTg, LUTh, HHg, HHh, pos, residues
+    static constexpr int GROUP_INTS = 8 * P + 2 * H + 2 * PG_MAX_SEQ;
 };
 
 // Per-CTA copy of the pair metadata (avoids divergent constant-bank indexing).
@@ -61,53 +61,82 @@ __device__ __forceinline__ void pg_load_pair_meta(const DevProblem &p, PairMeta 
     }
 }
 
-// Expand one parent with a group of LP lanes.  `sub` is the lane's index in the
-// group and its low mask bits, `gmask` the shfl mask of the group's lanes.
+// Per-lane result of the factorisation for one parent.
+template <int N>
+struct ExpLane {
+    int Bg, Bh;                                       // B[low] (Bg already includes the parent's g)
+    int Eg[ExpCfg<N>::HB > 0 ? ExpCfg<N>::HB : 1];    // E_y[low] per high sequence
+    int Eh[ExpCfg<N>::HB > 0 ? ExpCfg<N>::HB : 1];
+    int alive;                                        // sequences that can still advance (borderCheck, Node.cpp:69-77)
+};
+
+// Stage the LUTs / HH table of one parent in the group's shared memory and compute the lane's B and E terms.
+// `sub` is the lane's index in the group and its low mask bits, `gmask` the shfl mask of the group's lanes.
 // s_grp points at GROUP_INTS ints of shared memory private to the group.
-// The sink is called once per valid successor:
-//   sink(mask, idx, posn, gnew, hnew)   idx = rank of mask among the valid masks (ascending)
-template <int N, class Sink>
-__device__ __forceinline__ void pg_expand_parent(const DevProblem &p, const PairMeta *meta, int *s_grp, const int (&pos)[N],
-                                                 int g, int parenti, int sub, unsigned gmask, Sink &sink)
+template <int N>
+__device__ __forceinline__ void pg_expand_prepare(const DevProblem &p, const PairMeta *meta, int *s_grp, const int (&pos)[N], int g,
+                                                  int parenti, int sub, unsigned gmask, ExpLane<N> &L)
 {
     using C = ExpCfg<N>;
     int *s_lutg = s_grp;
     int *s_luth = s_grp + 4 * C::P;
     int *s_hhg = s_grp + 8 * C::P;
     int *s_hhh = s_hhg + C::H;
-    int *s_pos = s_hhh + C::H;
+    int *s_pos = s_hhh + C::H; // N positions, then N residues
 
-    if (sub == 0) {
-#pragma unroll
-        for (int i = 0; i < N; i++) s_pos[i] = pos[i];
-    }
-    int alive = 0; // sequences that can still advance (borderCheck, Node.cpp:69-77)
+    int alive = 0;
 #pragma unroll
     for (int i = 0; i < N; i++) alive |= (pos[i] < p.len[i]) << i;
+    L.alive = alive;
+    if (sub < N) {
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (i == sub) v = pos[i];
+        s_pos[sub] = v;
+        s_pos[PG_MAX_SEQ + sub] = (int)__ldg(p.seq[sub] + v); // Node.cpp:225 reads seq[len] at the border: padded 0
+    }
     __syncwarp(gmask);
 
-    // ---- per-pair LUTs: 4*P entries, strided over the group's lanes
-    for (int e = sub; e < 4 * C::P; e += C::LP) {
-        const int pr = e >> 2, dx = e & 1, dy = (e >> 1) & 1;
-        const int x = meta->pa[pr], y = meta->pb[pr];
-        const int px = s_pos[x], py = s_pos[y];
-        const int w = meta->w[pr];
-        // moves that leave the lattice are never emitted; clamp so the gather stays in bounds
-        const int ix = min(px + dx, p.len[x]), iy = min(py + dy, p.len[y]);
-        const size_t cell = (size_t)ix * meta->cols[pr] + iy;
-        const int t = p.cell16 ? (int)__ldg(reinterpret_cast<const uint16_t *>(meta->table[pr]) + cell)
-                               : __ldg(reinterpret_cast<const int32_t *>(meta->table[pr]) + cell);
-        int c;
-        if (dx & dy)
-            c = __ldg(p.cost + (int)__ldg(p.seq[x] + px) * 90 + (int)__ldg(p.seq[y] + py)); // Node.cpp:225
-        else if (dx)
-            c = ((parenti >> y) & 1) ? p.gap_open : p.gap_ext; // gap in y, Node.cpp:140,149-151
-        else if (dy)
-            c = ((parenti >> x) & 1) ? p.gap_open : p.gap_ext; // gap in x
-        else
-            c = p.gap_gap; // Node.cpp:142
-        s_lutg[e] = c * w;
-        s_luth[e] = t * w;
+    // ---- per-pair LUTs: 4*P entries strided over the group's lanes.  All gathers are issued first (no shared
+    //      stores in between), so the L2 latencies of a lane's entries overlap.
+    constexpr int NE = (4 * C::P + C::LP - 1) / C::LP;
+    int tv[NE], cv[NE];
+#pragma unroll
+    for (int j = 0; j < NE; j++) {
+        const int e = sub + j * C::LP;
+        tv[j] = 0;
+        cv[j] = 0;
+        if (e < 4 * C::P) {
+            const int pr = e >> 2, dx = e & 1, dy = (e >> 1) & 1;
+            const int x = meta->pa[pr], y = meta->pb[pr];
+            // moves that leave the lattice are never emitted; clamp so the gather stays in bounds
+            const int ix = min(s_pos[x] + dx, p.len[x]), iy = min(s_pos[y] + dy, p.len[y]);
+            const size_t cell = (size_t)ix * meta->cols[pr] + iy;
+            tv[j] = p.cell16 ? (int)__ldg(reinterpret_cast<const uint16_t *>(meta->table[pr]) + cell)
+                             : __ldg(reinterpret_cast<const int32_t *>(meta->table[pr]) + cell);
+            if (dx & dy) cv[j] = __ldg(p.cost + s_pos[PG_MAX_SEQ + x] * 90 + s_pos[PG_MAX_SEQ + y]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NE; j++) {
+        const int e = sub + j * C::LP;
+        if (e < 4 * C::P) {
+            const int pr = e >> 2, dx = e & 1, dy = (e >> 1) & 1;
+            const int x = meta->pa[pr], y = meta->pb[pr];
+            const int w = meta->w[pr];
+            int c;
+            if (dx & dy)
+                c = cv[j]; // match / mismatch
+            else if (dx)
+                c = ((parenti >> y) & 1) ? p.gap_open : p.gap_ext; // gap in y, Node.cpp:140,149-151
+            else if (dy)
+                c = ((parenti >> x) & 1) ? p.gap_open : p.gap_ext; // gap in x
+            else
+                c = p.gap_gap; // Node.cpp:142
+            s_lutg[e] = c * w;
+            s_luth[e] = tv[j] * w;
+        }
     }
     __syncwarp(gmask);
 
@@ -140,7 +169,6 @@ __device__ __forceinline__ void pg_expand_parent(const DevProblem &p, const Pair
             Bh += s_luth[idx];
         }
     }
-    int Eg[C::HB > 0 ? C::HB : 1], Eh[C::HB > 0 ? C::HB : 1];
 #pragma unroll
     for (int y = C::A; y < N; y++) {
         int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
@@ -155,38 +183,76 @@ __device__ __forceinline__ void pg_expand_parent(const DevProblem &p, const Pair
         }
         Bg += g0;
         Bh += h0;
-        Eg[y - C::A] = g1 - g0;
-        Eh[y - C::A] = h1 - h0;
+        L.Eg[y - C::A] = g1 - g0;
+        L.Eh[y - C::A] = h1 - h0;
     }
+    L.Bg = Bg;
+    L.Bh = Bh;
     __syncwarp(gmask);
+}
 
-    // ---- enumerate the high bits
+// rank of `mask` among the submasks of `alive` in ascending order, minus one (compress mask onto alive's bits)
+template <int N>
+__device__ __forceinline__ int pg_mask_rank(int mask, int alive)
+{
+    int r = 0, o = 0;
+#pragma unroll
+    for (int b = 0; b < N; b++) {
+        if ((alive >> b) & 1) {
+            r |= ((mask >> b) & 1) << o;
+            o++;
+        }
+    }
+    return r - 1;
+}
+
+// g / h sums of the 2^IB masks that share the upper high bits `u`, by recursive doubling in registers
+template <int N>
+__device__ __forceinline__ void pg_expand_block(const ExpLane<N> &L, int u, int (&vg)[1 << ExpCfg<N>::IB], int (&vh)[1 << ExpCfg<N>::IB])
+{
+    using C = ExpCfg<N>;
+    vg[0] = L.Bg;
+    vh[0] = L.Bh;
+#pragma unroll
+    for (int b = 0; b < C::UB; b++) {
+        if ((u >> b) & 1) {
+            vg[0] += L.Eg[C::IB + b];
+            vh[0] += L.Eh[C::IB + b];
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < C::IB; b++) {
+#pragma unroll
+        for (int i = 0; i < (1 << b); i++) {
+            vg[i + (1 << b)] = vg[i] + L.Eg[b];
+            vh[i + (1 << b)] = vh[i] + L.Eh[b];
+        }
+    }
+}
+
+// Expand one parent with a group of LP lanes.  The sink is called once per valid successor:
+//   sink(mask, idx, posn, gnew, hnew)   idx = rank of mask among the valid masks (ascending)
+template <int N, class Sink>
+__device__ __forceinline__ void pg_expand_parent(const DevProblem &p, const PairMeta *meta, int *s_grp, const int (&pos)[N],
+                                                 int g, int parenti, int sub, unsigned gmask, Sink &sink)
+{
+    using C = ExpCfg<N>;
+    const int *s_hhg = s_grp + 8 * C::P;
+    const int *s_hhh = s_hhg + C::H;
+    ExpLane<N> L;
+    pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
+
     int posn[N];
 #pragma unroll
     for (int i = 0; i < C::A; i++) posn[i] = pos[i] + ((sub >> i) & 1);
     const int full = (1 << N) - 1;
-    const bool interior = alive == full;
+    const bool interior = L.alive == full;
 
     for (int u = 0; u < (1 << C::UB); u++) {
         int vg[1 << C::IB], vh[1 << C::IB];
-        vg[0] = Bg;
-        vh[0] = Bh;
+        pg_expand_block<N>(L, u, vg, vh);
 #pragma unroll
-        for (int b = 0; b < C::UB; b++) {
-            if ((u >> b) & 1) {
-                vg[0] += Eg[C::IB + b];
-                vh[0] += Eh[C::IB + b];
-            }
-            posn[C::A + C::IB + b] = pos[C::A + C::IB + b] + ((u >> b) & 1);
-        }
-#pragma unroll
-        for (int b = 0; b < C::IB; b++) {
-#pragma unroll
-            for (int i = 0; i < (1 << b); i++) {
-                vg[i + (1 << b)] = vg[i] + Eg[b];
-                vh[i + (1 << b)] = vh[i] + Eh[b];
-            }
-        }
+        for (int b = 0; b < C::UB; b++) posn[C::A + C::IB + b] = pos[C::A + C::IB + b] + ((u >> b) & 1);
 #pragma unroll
         for (int i = 0; i < (1 << C::IB); i++) {
             const int high = (u << C::IB) | i;
@@ -194,19 +260,8 @@ __device__ __forceinline__ void pg_expand_parent(const DevProblem &p, const Pair
 #pragma unroll
             for (int b = 0; b < C::IB; b++) posn[C::A + b] = pos[C::A + b] + ((i >> b) & 1);
             if (mask == 0) continue;
-            if (!interior && (mask & ~alive)) continue;
-            int idx = mask - 1;
-            if (!interior) { // rank among the submasks of `alive`: compress the mask onto alive's bits
-                int r = 0, o = 0;
-#pragma unroll
-                for (int b = 0; b < N; b++) {
-                    if ((alive >> b) & 1) {
-                        r |= ((mask >> b) & 1) << o;
-                        o++;
-                    }
-                }
-                idx = r - 1;
-            }
+            if (!interior && (mask & ~L.alive)) continue;
+            const int idx = interior ? mask - 1 : pg_mask_rank<N>(mask, L.alive);
             sink(mask, idx, posn, vg[i] + s_hhg[high], vh[i] + s_hhh[high]);
         }
     }

@@ -62,6 +62,7 @@ struct SearchState {
     uint64_t *d_table = nullptr;
     unsigned long long *d_buckets = nullptr;
     uint32_t *d_tail = nullptr;              // per bucket: entries in the chunks behind the head
+    uint32_t *d_hint = nullptr;
     uint32_t *d_pool = nullptr;
     unsigned long long *d_link = nullptr;    // per unit: {offset, lg} of the previous chunk of the bucket
     uint32_t n_units = 0;
@@ -172,6 +173,7 @@ struct DevSearch {
     unsigned long long cap_mask;
     unsigned long long *buckets;
     uint32_t *tail;
+    uint32_t *hint; // per bucket: log2 units of the largest chunk it ever had
     uint32_t *pool;
     unsigned long long *link;
     uint32_t n_units;
@@ -185,8 +187,8 @@ struct DevSearch {
     unsigned long long outbox_cap;
 };
 
-struct Counters {
-    unsigned long long expansions, generated, reopen, inserted, pushed, pruned, stale;
+struct Counters { // per thread, flushed once per kernel
+    unsigned expansions, generated, reopen, inserted, pushed, pruned, stale;
 };
 
 // Find / claim the table slot of a key.  Returns the slot (entry index) or ~0 when the table is full.
@@ -273,18 +275,21 @@ __device__ __forceinline__ void bucket_push(const DevSearch &d, int f, uint32_t 
             return;
         }
         if (cnt == capn) {
-            const uint32_t nlg = off == CHUNK_NONE ? 0u : min(lg + 1u, MAXLG);
+            // First chunk of a (re)filled bucket: as large as the bucket grew last time (d.hint), so a hot bucket is
+            // not re-grown 64, 128, ... every round.  Pushers that lost the race poll until the new head is published,
+            // so the critical section is only bump + publish; bookkeeping that only the select kernel reads comes after.
+            const uint32_t nlg = off == CHUNK_NONE ? min(d.hint[b], MAXLG) : min(lg + 1u, MAXLG);
             const uint32_t nc = atomicAdd(&c->chunk_bump, 1u << nlg);
             if ((unsigned long long)nc + (1u << nlg) > d.n_units) {
                 c->error = 2;
                 atomicExch(bk, bucket_pack(off, lg, capn)); // leave the bucket consistent
                 return;
             }
+            atomicExch(bk, bucket_pack(nc, nlg, 1u));
             d.link[nc] = ((unsigned long long)off << 32) | lg;
             d.pool[(size_t)nc * UNIT] = slot;
             if (off != CHUNK_NONE) atomicAdd(&d.tail[b], capn);
-            __threadfence();
-            atomicExch(bk, bucket_pack(nc, nlg, 1u));
+            if (nlg > d.hint[b]) d.hint[b] = nlg;
             return;
         }
     }
@@ -433,103 +438,135 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, lon
 // ---------------------------------------------------------------------------------------------
 // fused expand + owner + dedupe + push
 // ---------------------------------------------------------------------------------------------
-template <int N, int KEYW>
-struct ProbeSink {
-    using C = ExpCfg<N>;
-    const DevSearch &d;
-    const DevProblem &p;
-    const Key<KEYW> *s_keyhigh; // shared: key delta of each high mask
-    Key<KEYW> klow;             // parent key + this lane's low mask bits
-    int limit;                  // prune successors with f >= limit
-    int goal_mask;              // the move mask that reaches the final coordinate from this parent (0 if none)
-    Counters &cn;
-    // owner plan (multi-partition)
-    int own_type, own_shift, own_nb;
-    int own_sh[8];
-
-    __device__ __forceinline__ void operator()(int mask, int idx, const int (&posn)[N], int gnew, int hnew)
-    {
-        (void)idx;
-        const int f = gnew + hnew;
-        cn.generated++;
-        const bool is_goal = mask == goal_mask;
-        if (is_goal) atomicMin(&d.ctrl->best_goal, gnew);
-        if (f >= limit && !is_goal) {
-            cn.pruned++;
-            return;
-        }
-        const Key<KEYW> key = klow.plus(s_keyhigh[mask >> C::A]);
-        if (d.n_parts > 1) {
-            unsigned own;
-            if (own_type == PG_HASH_FSUM) {
-                unsigned s = 0;
-#pragma unroll
-                for (int i = 0; i < N; i++) s += posn[i];
-                own = (s >> own_shift) % (unsigned)d.n_parts;
-            } else if (own_type == PG_HASH_PSUM) {
-                own = ((unsigned)(posn[0] + posn[1]) >> own_shift) % (unsigned)d.n_parts;
-            } else {
-                unsigned w = 0;
-                for (int m = 0; m < own_nb; m++)
-                    if (own_sh[m] >= 0) w |= key.field(own_sh[m], 1u) << m;
-                own = w % (unsigned)d.n_parts;
-            }
-            if ((int)own != d.part) {
-                // remote successor: append {key, g, f, parenti} to the owner's outbox
-                const unsigned long long pos = atomicAdd(&d.outbox_count[own], 1ull);
-                if (pos >= d.outbox_cap) {
-                    d.ctrl->error = 4;
-                    return;
-                }
-                constexpr int XW = KEYW == 1 ? 3 : 4; // u64 words per record
-                unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) + ((size_t)own * d.outbox_cap + pos) * XW;
-                r[0] = key.lo;
-                if constexpr (KEYW == 2) r[1] = key.hi;
-                r[KEYW] = ((unsigned long long)(unsigned)gnew << 32) | (unsigned)f;
-                r[KEYW + 1] = (unsigned long long)(unsigned)mask;
-                return;
-            }
-        }
-        upsert(key, gnew, f, mask);
-    }
-
-    __device__ __forceinline__ void upsert(const Key<KEYW> &key, int gnew, int f, int mask)
-    {
-        unsigned long long val;
-        bool fresh;
-        const unsigned long long slot = table_slot<KEYW>(d, key, val, fresh);
-        if (slot == ~0ull) {
-            d.ctrl->error = 1;
-            return;
-        }
-        if (fresh) cn.inserted++;
-        unsigned long long *vp = val_ptr<KEYW>(d, slot);
-        const unsigned long long mine = ~(((unsigned long long)(unsigned)gnew << 32) | OPEN_BIT | (unsigned long long)(unsigned)mask);
-        for (;;) {
-            const unsigned g_old = (unsigned)((~val) >> 32); // 0xffffffff for a fresh entry
-            if ((unsigned)gnew >= g_old) return;             // PAStar.cpp:228 / PriorityList.h:109: not better, drop
-            const unsigned long long prev = atomicCAS(vp, val, mine);
-            if (prev == val) break;
-            val = prev;
-        }
-        if (val != 0 && !((~val) & OPEN_BIT)) cn.reopen++; // was closed with a worse g: PAStar.cpp:230-231
-        cn.pushed++;
-        bucket_push(d, f, (uint32_t)slot);
-    }
+// Structure of one CTA (256 threads), per tile of 256 popped open-list entries:
+//   stage 0  one thread per entry: plan lookup, table entry load, closed-bit claim (PAStar.cpp:344-351); entries
+//            that are stale (a better g was pushed later) or already closed drop out here, live ones are compacted
+//            into shared memory, so the expansion below only sees nodes that are really expanded.
+//   stage 1  a group of 2^A lanes per live parent: LUT / HH staging (pg_expand_prepare), then per lane
+//            pass 1: compute f, g, key, hash slot of its next successors and ISSUE all their table loads (up to 8
+//                    independent 16 B loads in flight per lane: the probe is latency-bound, not bandwidth-bound);
+//            pass 2: compare.  The common case (same key, g not better: PAStar.cpp:228 / PriorityList.h:109)
+//                    ends here with no atomic and no store.  The rest - new key, better g, hash collision -
+//                    is appended to a per-warp shared-memory queue and
+//            drain:  executed 32 items at a time with all lanes active (CAS on key / value, push to the f bucket),
+//                    so the rare slow path does not serialise the warp.
+struct OwnerArgs {
+    int type, shift, nb;
+    int sh[8];
 };
 
+template <int KEYW>
+struct SlowQ {
+    static constexpr int IW = KEYW == 1 ? 4 : 6; // u64 words per item
+    static constexpr int CAP = 64;               // items per warp (ring)
+};
+
+// slow path for one successor: find/claim its slot starting at `slot`, install g if strictly better, push.
+template <int KEYW>
+__device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> &key, unsigned long long slot, int gnew, int f, int mask,
+                                            Counters &cn)
+{
+    constexpr int ES = KEYW == 1 ? 2 : 4;
+    unsigned long long val = 0;
+    bool found = false;
+    for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+        unsigned long long *e = d.table + slot * ES;
+        if constexpr (KEYW == 1) {
+            unsigned long long k, v;
+            ld_cg_v2(e, k, v);
+            if (k == key.lo + 1) {
+                val = v;
+                found = true;
+                break;
+            }
+            if (k != 0) continue;
+            const unsigned long long prev = atomicCAS(e, 0ull, key.lo + 1);
+            if (prev == 0) {
+                cn.inserted++;
+                val = 0;
+                found = true;
+                break;
+            }
+            if (prev == key.lo + 1) {
+                val = ld_cg_u64(e + 1);
+                found = true;
+                break;
+            }
+        } else {
+            unsigned long long k0, k1;
+            ld_cg_v2(e, k0, k1);
+            const unsigned long long want0 = key.lo, want1 = key.hi | (1ull << 63);
+            if (k0 == want0 && k1 == want1) {
+                val = ld_cg_u64(e + 2);
+                found = true;
+                break;
+            }
+            if (k0 != 0 || k1 != 0) continue;
+            unsigned long long p0, p1;
+            cas128(e, want0, want1, p0, p1);
+            if (p0 == 0 && p1 == 0) {
+                cn.inserted++;
+                val = 0;
+                found = true;
+                break;
+            }
+            if (p0 == want0 && p1 == want1) {
+                val = ld_cg_u64(e + 2);
+                found = true;
+                break;
+            }
+        }
+    }
+    if (!found) {
+        d.ctrl->error = 1;
+        return;
+    }
+    unsigned long long *vp = val_ptr<KEYW>(d, slot);
+    const unsigned long long mine = ~(((unsigned long long)(unsigned)gnew << 32) | OPEN_BIT | (unsigned long long)(unsigned)mask);
+    for (;;) {
+        const unsigned g_old = (unsigned)((~val) >> 32); // 0xffffffff for a fresh entry
+        if ((unsigned)gnew >= g_old) return;             // PAStar.cpp:228 / PriorityList.h:109: not better, drop
+        const unsigned long long prev = atomicCAS(vp, val, mine);
+        if (prev == val) break;
+        val = prev;
+    }
+    if (val != 0 && !((~val) & OPEN_BIT)) cn.reopen++; // was closed with a worse g: PAStar.cpp:230-231
+    cn.pushed++;
+    bucket_push(d, f, (uint32_t)slot);
+}
+
+template <int KEYW>
+__device__ __forceinline__ void drain_item(const DevSearch &d, const unsigned long long *it, Counters &cn)
+{
+    Key<KEYW> key;
+    key.lo = it[0];
+    if constexpr (KEYW == 2) key.hi = it[1];
+    const unsigned long long slot = it[KEYW], gf = it[KEYW + 1], m = it[KEYW + 2];
+    upsert_from<KEYW>(d, key, slot, (int)(unsigned)(gf >> 32), (int)(unsigned)gf, (int)(unsigned)m, cn);
+}
+
 template <int N, int KEYW>
-__global__ void __launch_bounds__(256) search_expand_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
-                                                            int own_nb, int own_sh0, int own_sh1, int own_sh2, int own_sh3,
-                                                            int own_sh4, int own_sh5, int own_sh6, int own_sh7)
+__global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
+                                                               const __grid_constant__ OwnerArgs oa)
 {
     using C = ExpCfg<N>;
+    using Q = SlowQ<KEYW>;
+    constexpr int GROUPS = 256 / C::LP;
+    constexpr int NI = 1 << C::IB;
+    constexpr int PFMAX = KEYW == 1 ? 8 : 4;
+    constexpr int PF = NI < PFMAX ? NI : PFMAX; // successors whose table loads are in flight together, per lane
+    constexpr int PLAN_SM = 1024;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairMeta *meta = reinterpret_cast<PairMeta *>(smem_raw);
     Key<KEYW> *s_keyhigh = reinterpret_cast<Key<KEYW> *>(smem_raw + ((sizeof(PairMeta) + 15) & ~size_t(15)));
-    int *s_groups = reinterpret_cast<int *>(s_keyhigh + C::H);
-    __shared__ unsigned long long s_cnt[7];
+    unsigned long long *s_tkey = reinterpret_cast<unsigned long long *>(s_keyhigh + C::H); // [KEYW][256]
+    unsigned long long *s_tval = s_tkey + KEYW * 256;
+    unsigned long long *s_queue = s_tval + 256; // [8 warps][CAP][IW]
+    uint32_t *s_plan = reinterpret_cast<uint32_t *>(s_queue + 8 * Q::CAP * Q::IW);
+    int *s_groups = reinterpret_cast<int *>(s_plan + PLAN_SM);
+    __shared__ unsigned long long s_cnt[8];
     __shared__ int s_ctl[4];
+    __shared__ int s_tcount;
 
     SearchCtrl *c = d.ctrl;
     if (threadIdx.x == 0) { // one reader, so the whole CTA takes the same early exit
@@ -542,6 +579,7 @@ __global__ void __launch_bounds__(256) search_expand_kernel(const __grid_constan
     if (batch_n == 0) return;
     const int plan_n = s_ctl[1];
     const int limit = s_ctl[2];
+    const bool plan_sm = plan_n <= PLAN_SM;
 
     pg_load_pair_meta(p, meta);
     for (int hi = threadIdx.x; hi < C::H; hi += blockDim.x) {
@@ -550,88 +588,258 @@ __global__ void __launch_bounds__(256) search_expand_kernel(const __grid_constan
             if ((hi >> b) & 1) k.add_bit((C::A + b) * p.key_bits);
         s_keyhigh[hi] = k;
     }
-    if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
+    if (plan_sm)
+        for (int i = threadIdx.x; i < plan_n; i += blockDim.x) s_plan[i] = d.plan[i].offset;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     __syncthreads();
 
-    constexpr int GROUPS = 256 / C::LP;
     const int grp = threadIdx.x / C::LP, sub = threadIdx.x % C::LP;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned gmask = C::LP == 32 ? 0xffffffffu : (((1u << C::LP) - 1u) << (lane & ~(C::LP - 1)));
+    const unsigned lt = (1u << lane) - 1u;
     int *s_grp = s_groups + grp * C::GROUP_INTS;
+    const int *s_hhg = s_grp + 8 * C::P;
+    const int *s_hhh = s_hhg + C::H;
+    unsigned long long *wq = s_queue + (size_t)warp * Q::CAP * Q::IW;
+    unsigned qhead = 0, qtail = 0; // warp-uniform ring indices
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     const unsigned fmask = (1u << p.key_bits) - 1u;
+    const int full = (1 << N) - 1;
 
-    for (int base = blockIdx.x * GROUPS; base < batch_n; base += gridDim.x * GROUPS) {
-        const int bi = base + grp;
-        if (bi >= batch_n) continue;
-        // ---- lane 0 of the group: plan lookup, load the entry, claim it (closed check, PAStar.cpp:344-351)
-        unsigned long long klo = 0, khi = 0, val = 0;
-        int ok = 0;
-        if (sub == 0) {
-            int lo = 0, hi = plan_n - 1;
-            while (lo < hi) { // last entry with offset <= bi
-                const int mid = (lo + hi + 1) >> 1;
-                if ((int)d.plan[mid].offset <= bi)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            const PlanEntry pe = d.plan[lo];
-            const uint32_t slot = d.pool[(size_t)pe.unit * UNIT + pe.start + (bi - pe.offset)];
-            unsigned long long *e = d.table + (size_t)slot * (KEYW == 1 ? 2 : 4);
-            // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion
-            const unsigned long long old = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
-            if (!(old & OPEN_BIT)) {
-                ok = 1;
-                val = ~old;
-                if constexpr (KEYW == 1) {
-                    klo = ld_cg_u64(e) - 1;
-                } else {
-                    klo = ld_cg_u64(e);
-                    khi = ld_cg_u64(e + 1) & ~(1ull << 63);
+    for (int tbase = blockIdx.x * 256; tbase < batch_n; tbase += gridDim.x * 256) {
+        if (threadIdx.x == 0) s_tcount = 0;
+        __syncthreads();
+        // ---------------- stage 0: claim
+        {
+            const int bi = tbase + threadIdx.x;
+            bool live = false;
+            unsigned long long klo = 0, khi = 0, val = 0;
+            if (bi < batch_n) {
+                int lo = 0, hi = plan_n - 1;
+                while (lo < hi) { // last plan entry with offset <= bi
+                    const int mid = (lo + hi + 1) >> 1;
+                    const uint32_t off = plan_sm ? s_plan[mid] : d.plan[mid].offset;
+                    if ((int)off <= bi)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
                 }
-            } else {
-                cn.stale++;
+                const PlanEntry pe = d.plan[lo];
+                const uint32_t slot = d.pool[(size_t)pe.unit * UNIT + pe.start + (bi - pe.offset)];
+                unsigned long long *e = d.table + (size_t)slot * (KEYW == 1 ? 2 : 4);
+                // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion
+                const unsigned long long old = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
+                if (!(old & OPEN_BIT)) {
+                    live = true;
+                    val = ~old;
+                    if constexpr (KEYW == 1) {
+                        klo = ld_cg_u64(e) - 1;
+                    } else {
+                        klo = ld_cg_u64(e);
+                        khi = ld_cg_u64(e + 1) & ~(1ull << 63);
+                    }
+                } else {
+                    cn.stale++;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, live);
+            int wbase = 0;
+            if (lane == 0 && bal) wbase = atomicAdd(&s_tcount, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (live) {
+                const int idx = wbase + __popc(bal & lt);
+                s_tkey[idx] = klo;
+                if constexpr (KEYW == 2) s_tkey[256 + idx] = khi;
+                s_tval[idx] = val;
             }
         }
-        ok = __shfl_sync(gmask, ok, 0, C::LP);
-        if (!ok) continue;
-        klo = __shfl_sync(gmask, klo, 0, C::LP);
-        if constexpr (KEYW == 2) khi = __shfl_sync(gmask, khi, 0, C::LP);
-        val = __shfl_sync(gmask, val, 0, C::LP);
-        Key<KEYW> pkey;
-        pkey.lo = klo;
-        if constexpr (KEYW == 2) pkey.hi = khi;
-        const int g = (int)(unsigned)(val >> 32);
-        const int parenti = (int)(val & 0xffffu);
-        int pos[N];
-#pragma unroll
-        for (int i = 0; i < N; i++) pos[i] = (int)pkey.field(i * p.key_bits, fmask);
-        // the goal is reached from this parent by moving every sequence that is one short of its end
-        int alive = 0, onestep = 0;
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            alive |= (pos[i] < p.len[i]) << i;
-            onestep |= (pos[i] + 1 == p.len[i]) << i;
-        }
-        if (alive == 0) continue; // the goal itself: never expanded (PAStar.cpp:353-357)
-        if (sub == 0) cn.expansions++;
+        __syncthreads();
+        const int nlive = s_tcount;
+        const int iters = (nlive + GROUPS - 1) / GROUPS;
 
-        Key<KEYW> klow = pkey;
+        // ---------------- stage 1: expand the live parents
+        for (int it = 0; it < iters; it++) {
+            const int pi = it * GROUPS + grp;
+            bool act = pi < nlive;
+            Key<KEYW> pkey = Key<KEYW>::zero();
+            int pos[N];
+            int g = 0, parenti = 0, goal_mask = 0;
+            ExpLane<N> L;
+            L.alive = 0;
+            if (act) {
+                pkey.lo = s_tkey[pi];
+                if constexpr (KEYW == 2) pkey.hi = s_tkey[256 + pi];
+                const unsigned long long val = s_tval[pi];
+                g = (int)(unsigned)(val >> 32);
+                parenti = (int)(val & 0xffffu);
+                int alive = 0, onestep = 0;
 #pragma unroll
-        for (int i = 0; i < C::A; i++)
-            if ((sub >> i) & 1) klow.add_bit(i * p.key_bits);
-        ProbeSink<N, KEYW> sink{d, p, s_keyhigh, klow, limit, alive == onestep ? alive : 0, cn, p.hash_type, p.hash_shift, own_nb,
-                                {own_sh0, own_sh1, own_sh2, own_sh3, own_sh4, own_sh5, own_sh6, own_sh7}};
-        pg_expand_parent<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, sink);
+                for (int i = 0; i < N; i++) {
+                    pos[i] = (int)pkey.field(i * p.key_bits, fmask);
+                    alive |= (pos[i] < p.len[i]) << i;
+                    onestep |= (pos[i] + 1 == p.len[i]) << i;
+                }
+                if (alive == 0) {
+                    act = false; // the goal itself: never expanded (PAStar.cpp:353-357)
+                } else {
+                    // the goal is reached from here by moving every sequence that is one short of its end
+                    goal_mask = alive == onestep ? alive : 0;
+                    if (sub == 0) cn.expansions++;
+                    pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
+                }
+            }
+            Key<KEYW> klow = pkey;
+#pragma unroll
+            for (int i = 0; i < C::A; i++)
+                if ((sub >> i) & 1) klow.add_bit(i * p.key_bits);
+            const bool interior = L.alive == full;
+
+            for (int u = 0; u < (1 << C::UB); u++) {
+                int vg[NI], vh[NI];
+                pg_expand_block<N>(L, u, vg, vh);
+#pragma unroll
+                for (int cb = 0; cb < NI; cb += PF) {
+                    unsigned long long lk[PF], lv[PF];
+                    unsigned long long lw[KEYW == 2 ? PF : 1]; // KEYW=2: the value word
+                    uint32_t ls[PF];
+                    int lg[PF];
+                    unsigned vmask = 0;
+                    // ---- pass 1: issue the probes
+#pragma unroll
+                    for (int j = 0; j < PF; j++) {
+                        const int i = cb + j;
+                        const int high = (u << C::IB) | i;
+                        const int mask = (high << C::A) | sub;
+                        bool v = act && mask != 0 && (interior || !(mask & ~L.alive));
+                        lk[j] = lv[j] = 0;
+                        ls[j] = 0;
+                        lg[j] = 0;
+                        if (v) {
+                            const int gn = vg[i] + s_hhg[high];
+                            const int f = gn + vh[i] + s_hhh[high];
+                            cn.generated++;
+                            const bool is_goal = mask == goal_mask;
+                            if (is_goal) atomicMin(&c->best_goal, gn);
+                            if (f >= limit && !is_goal) {
+                                cn.pruned++;
+                                v = false;
+                            }
+                            lg[j] = gn;
+                        }
+                        if (v) {
+                            const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                            if (d.n_parts > 1) {
+                                unsigned own;
+                                if (oa.type == PG_HASH_FSUM || oa.type == PG_HASH_PSUM) {
+                                    unsigned s = 0;
+                                    const int nd = oa.type == PG_HASH_PSUM ? 2 : N;
+                                    for (int q = 0; q < nd; q++) s += key.field(q * p.key_bits, fmask);
+                                    own = (s >> oa.shift) % (unsigned)d.n_parts;
+                                } else {
+                                    unsigned w = 0;
+#pragma unroll
+                                    for (int m = 0; m < 8; m++)
+                                        if (m < oa.nb && oa.sh[m] >= 0) w |= key.field(oa.sh[m], 1u) << m;
+                                    own = w % (unsigned)d.n_parts;
+                                }
+                                if ((int)own != d.part) {
+                                    // remote successor: append {key, g, f, parenti} to the owner's outbox
+                                    const unsigned long long opos = atomicAdd(&d.outbox_count[own], 1ull);
+                                    if (opos >= d.outbox_cap) {
+                                        c->error = 4;
+                                    } else {
+                                        constexpr int XW = KEYW == 1 ? 3 : 4;
+                                        unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) + ((size_t)own * d.outbox_cap + opos) * XW;
+                                        const int f = lg[j] + vh[i] + s_hhh[high];
+                                        r[0] = key.lo;
+                                        if constexpr (KEYW == 2) r[1] = key.hi;
+                                        r[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)f;
+                                        r[KEYW + 1] = (unsigned long long)(unsigned)mask;
+                                    }
+                                    v = false;
+                                }
+                            }
+                            if (v) {
+                                const unsigned long long slot = key.hash() & d.cap_mask;
+                                ls[j] = (uint32_t)slot;
+                                const unsigned long long *e = d.table + slot * (KEYW == 1 ? 2 : 4);
+                                if constexpr (KEYW == 1) {
+                                    ld_cg_v2(e, lk[j], lv[j]);
+                                } else {
+                                    ld_cg_v2(e, lk[j], lv[j]); // 32 B entry {k0, k1, val, pad}
+                                    lw[j] = ld_cg_u64(e + 2);
+                                }
+                                vmask |= 1u << j;
+                            }
+                        }
+                    }
+                    // ---- pass 2: classify; queue what needs an atomic
+#pragma unroll
+                    for (int j = 0; j < PF; j++) {
+                        const int i = cb + j;
+                        const int high = (u << C::IB) | i;
+                        const int mask = (high << C::A) | sub;
+                        bool slow = false;
+                        unsigned long long start = ls[j];
+                        Key<KEYW> key = Key<KEYW>::zero();
+                        if ((vmask >> j) & 1u) {
+                            key = klow.plus(s_keyhigh[high]);
+                            if constexpr (KEYW == 1) {
+                                if (lk[j] == key.lo + 1) {
+                                    const unsigned g_old = (unsigned)((~lv[j]) >> 32);
+                                    slow = (unsigned)lg[j] < g_old; // better g: needs the CAS
+                                } else {
+                                    slow = true; // empty slot or collision
+                                    if (lk[j] != 0) start = (start + 1) & d.cap_mask;
+                                }
+                            } else {
+                                if (lk[j] == key.lo && lv[j] == (key.hi | (1ull << 63))) {
+                                    const unsigned g_old = (unsigned)((~lw[j]) >> 32);
+                                    slow = (unsigned)lg[j] < g_old;
+                                } else {
+                                    slow = true;
+                                    if (lk[j] != 0 || lv[j] != 0) start = (start + 1) & d.cap_mask;
+                                }
+                            }
+                        }
+                        const unsigned sb = __ballot_sync(0xffffffffu, slow);
+                        if (sb) {
+                            if (slow) {
+                                unsigned long long *q = wq + (size_t)((qtail + __popc(sb & lt)) & (Q::CAP - 1)) * Q::IW;
+                                q[0] = key.lo;
+                                if constexpr (KEYW == 2) q[1] = key.hi;
+                                q[KEYW] = start;
+                                q[KEYW + 1] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)(lg[j] + vh[i] + s_hhh[high]);
+                                q[KEYW + 2] = (unsigned long long)(unsigned)mask;
+                            }
+                            qtail += __popc(sb);
+                            __syncwarp();
+                            if (qtail - qhead >= 32u) { // drain 32 items with every lane busy
+                                drain_item<KEYW>(d, wq + (size_t)((qhead + lane) & (Q::CAP - 1)) * Q::IW, cn);
+                                qhead += 32u;
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp(); // the group's LUTs are rewritten by the next parent
+        }
+        __syncthreads(); // tile arrays are rewritten by the next stage 0
     }
+    // ---------------- drain what is left in the warp's queue
+    if (lane < (int)(qtail - qhead)) drain_item<KEYW>(d, wq + (size_t)((qhead + lane) & (Q::CAP - 1)) * Q::IW, cn);
+
     // ---- counters: one atomic per CTA per counter
-    atomicAdd(&s_cnt[0], cn.expansions);
-    atomicAdd(&s_cnt[1], cn.generated);
-    atomicAdd(&s_cnt[2], cn.reopen);
-    atomicAdd(&s_cnt[3], cn.inserted);
-    atomicAdd(&s_cnt[4], cn.pushed);
-    atomicAdd(&s_cnt[5], cn.pruned);
+    {
+        unsigned v[6] = {cn.expansions, cn.generated, cn.reopen, cn.inserted, cn.pushed, cn.pruned};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            unsigned x = v[k];
+            for (int o = 16; o; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0 && x) atomicAdd(&s_cnt[k], (unsigned long long)x);
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         atomicAdd(&c->expansions, s_cnt[0]);
@@ -649,7 +857,7 @@ __global__ void insert_kernel(const __grid_constant__ DevSearch d, const unsigne
 {
     constexpr int XW = KEYW == 1 ? 3 : 4;
     SearchCtrl *c = d.ctrl;
-    unsigned long long inserted = 0, pushed = 0, reopen = 0;
+    Counters cn = {0, 0, 0, 0, 0, 0, 0};
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const unsigned long long *r = recs + i * XW;
         Key<KEYW> key;
@@ -661,32 +869,9 @@ __global__ void insert_kernel(const __grid_constant__ DevSearch d, const unsigne
         if constexpr (KEYW == 2) is_goal = is_goal && key.hi == d.goal_hi;
         if (is_goal) atomicMin(&c->best_goal, gnew);
         if (f >= min(c->prune_limit, c->best_goal) && !is_goal) continue;
-        unsigned long long val;
-        bool fresh;
-        const unsigned long long slot = table_slot<KEYW>(d, key, val, fresh);
-        if (slot == ~0ull) {
-            c->error = 1;
-            continue;
-        }
-        if (fresh) inserted++;
-        unsigned long long *vp = val_ptr<KEYW>(d, slot);
-        const unsigned long long mine = ~(((unsigned long long)(unsigned)gnew << 32) | OPEN_BIT | (unsigned long long)(unsigned)mask);
-        bool won = false;
-        for (;;) {
-            const unsigned g_old = (unsigned)((~val) >> 32);
-            if ((unsigned)gnew >= g_old) break;
-            const unsigned long long prev = atomicCAS(vp, val, mine);
-            if (prev == val) {
-                won = true;
-                break;
-            }
-            val = prev;
-        }
-        if (!won) continue;
-        if (val != 0 && !((~val) & OPEN_BIT)) reopen++;
-        pushed++;
-        bucket_push(d, f, (uint32_t)slot);
+        upsert_from<KEYW>(d, key, key.hash() & d.cap_mask, gnew, f, mask, cn);
     }
+    const unsigned long long inserted = cn.inserted, pushed = cn.pushed, reopen = cn.reopen;
     if (inserted) atomicAdd(&c->inserted, inserted);
     if (pushed) atomicAdd(&c->pushed, pushed);
     if (reopen) atomicAdd(&c->reopen, reopen);
@@ -881,6 +1066,7 @@ DevSearch dev_search(const pg_ctx *ctx)
     d.cap_mask = s->cap - 1;
     d.buckets = s->d_buckets;
     d.tail = s->d_tail;
+    d.hint = s->d_hint;
     d.pool = s->d_pool;
     d.link = s->d_link;
     d.n_units = s->n_units;
@@ -905,29 +1091,32 @@ template <int N, int KEYW>
 int launch_expand_round(pg_ctx *ctx, cudaStream_t st)
 {
     using C = ExpCfg<N>;
+    using Q = SlowQ<KEYW>;
     SearchState *s = ctx->search;
     constexpr int GROUPS = 256 / C::LP;
-    const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
+    const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + 8 * (KEYW + 1) * 256 + 8 * 8 * Q::CAP * Q::IW +
+                        4 * 1024 + sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
     static int occ = 0;
     if (!occ) {
         PG_CUDA(ctx, cudaFuncSetAttribute(search_expand_kernel<N, KEYW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_expand_kernel<N, KEYW>, 256, smem));
         if (occ < 1) occ = 1;
     }
-    // persistent grid: resident CTAs per SM x SM count, capped by the work of a full batch
+    // persistent grid: resident CTAs per SM x SM count, capped by the tiles of a full batch
     long long grid = (long long)ctx->sm_count * occ;
-    const long long want = (s->batch_target + GROUPS - 1) / GROUPS;
+    const long long want = (s->batch_target + 255) / 256;
     if (grid > want) grid = std::max<long long>(1, want);
-    int sh[8];
+    OwnerArgs oa;
+    oa.type = ctx->dp.hash_type;
+    oa.shift = ctx->dp.hash_shift;
     const int nd = ctx->dp.hash_type == PG_HASH_PZORDER ? 2 : ctx->n;
     for (int m = 0; m < 8; m++) {
         const int q = ctx->dp.hash_shift + m;
         const int coord = q % nd, bit = q / nd;
-        sh[m] = bit < ctx->dp.key_bits ? coord * ctx->dp.key_bits + bit : -1;
+        oa.sh[m] = bit < ctx->dp.key_bits ? coord * ctx->dp.key_bits + bit : -1;
     }
-    const int nb = std::min(8, ilog2i(std::max(1, s->cfg.n_parts)) + 2);
-    search_expand_kernel<N, KEYW><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, dev_search(ctx), nb, sh[0], sh[1], sh[2], sh[3], sh[4], sh[5],
-                                                                     sh[6], sh[7]);
+    oa.nb = std::min(8, ilog2i(std::max(1, s->cfg.n_parts)) + 2);
+    search_expand_kernel<N, KEYW><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, dev_search(ctx), oa);
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
 }
@@ -1034,6 +1223,7 @@ void pg_search_free(pg_ctx *ctx)
     cudaFree(s->d_table);
     cudaFree(s->d_buckets);
     cudaFree(s->d_tail);
+    cudaFree(s->d_hint);
     cudaFree(s->d_pool);
     cudaFree(s->d_link);
     cudaFree(s->d_plan);
@@ -1116,11 +1306,13 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     PG_CUDA(ctx, cudaMalloc(&s->d_buckets, (size_t)s->f_range * 8));
     PG_CUDA(ctx, cudaMalloc(&s->d_tail, (size_t)s->f_range * 4));
     PG_CUDA(ctx, cudaMemsetAsync(s->d_tail, 0, (size_t)s->f_range * 4, ctx->stream));
+    PG_CUDA(ctx, cudaMalloc(&s->d_hint, (size_t)s->f_range * 4));
+    PG_CUDA(ctx, cudaMemsetAsync(s->d_hint, 0, (size_t)s->f_range * 4, ctx->stream));
     fill_u64_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(s->d_buckets, BUCKET_EMPTY, (long long)s->f_range);
     PG_CUDA(ctx, cudaGetLastError());
     // Every table slot is pushed once per improvement.  Chunk sizes double, so a bucket wastes at most its own
     // size; each non-empty bucket holds at least one unit.
-    uint64_t units = 2 * (cap / UNIT) + (uint64_t)s->f_range + 4096;
+    uint64_t units = 3 * (cap / UNIT) + (uint64_t)s->f_range + 4096;
     s->n_units = (uint32_t)std::min<uint64_t>(units, 0x7ffffff0ull);
     PG_CUDA(ctx, cudaMalloc(&s->d_pool, (size_t)s->n_units * UNIT * 4));
     PG_CUDA(ctx, cudaMalloc(&s->d_link, (size_t)s->n_units * 8));
