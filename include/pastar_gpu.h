@@ -79,8 +79,9 @@ int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens, const int
 void pg_ctx_destroy(pg_ctx *ctx);
 const char *pg_last_error(const pg_ctx *ctx);
 int pg_abi_version(void);
-/* Run every later launch of this context on the caller's stream (cudaStream_t as void*; NULL = the
- * context's own stream), e.g. torch's current stream so that the caller's CUDA events bracket the work. */
+/* Run every later launch of this context on the caller's stream (cudaStream_t as void*; NULL = the legacy
+ * default stream as everywhere in CUDA, (void*)-1 = back to the context's own non-blocking stream), e.g. torch's
+ * current stream so that the caller's CUDA events bracket the work and NCCL collectives are ordered with it. */
 int pg_ctx_set_stream(pg_ctx *ctx, void *stream);
 
 /* ------------------------------------------------------------------ (1) pairwise DP heuristic */

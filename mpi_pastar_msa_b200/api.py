@@ -298,8 +298,8 @@ class PastarGPU:
         self._ck(self.L.pg_search_profile(self.h, 1 if enable else 0))
 
     def set_stream(self, stream):
-        """cudaStream_t handle (int) the context launches on; 0/None = its own stream."""
-        self._ck(self.L.pg_ctx_set_stream(self.h, stream or None))
+        """cudaStream_t handle (int) the context launches on; 0 = the legacy default stream (torch's default), -1 = own."""
+        self._ck(self.L.pg_ctx_set_stream(self.h, C.c_void_p(stream if stream != -1 else 2**64 - 1)))
 
     def search_outbox(self, dst):
         p, n = C.c_void_p(), C.c_int64()

@@ -164,7 +164,8 @@ extern "C" void pg_ctx_destroy(pg_ctx *ctx)
 extern "C" int pg_ctx_set_stream(pg_ctx *ctx, void *stream)
 {
     if (!ctx) return PG_ERR_ARG;
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    // NULL is the legacy default stream, as everywhere in CUDA (torch's default stream has handle 0); (void*)-1 = own
+    ctx->stream = stream == (void *)-1 ? ctx->own_stream : (stream ? (cudaStream_t)stream : cudaStreamLegacy);
     return PG_OK;
 }
 

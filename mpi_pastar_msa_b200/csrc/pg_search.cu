@@ -858,6 +858,7 @@ __global__ void insert_kernel(const __grid_constant__ DevSearch d, const unsigne
     constexpr int XW = KEYW == 1 ? 3 : 4;
     SearchCtrl *c = d.ctrl;
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
+    int min_b = INT_MAX;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const unsigned long long *r = recs + i * XW;
         Key<KEYW> key;
@@ -869,8 +870,14 @@ __global__ void insert_kernel(const __grid_constant__ DevSearch d, const unsigne
         if constexpr (KEYW == 2) is_goal = is_goal && key.hi == d.goal_hi;
         if (is_goal) atomicMin(&c->best_goal, gnew);
         if (f >= min(c->prune_limit, c->best_goal) && !is_goal) continue;
+        const unsigned before = cn.pushed;
         upsert_from<KEYW>(d, key, key.hash() & d.cap_mask, gnew, f, mask, cn);
+        if (cn.pushed != before) min_b = min(min_b, f - c->f0);
     }
+    // A node from another partition may have a lower f than anything open here (or this partition's open list may
+    // have run empty): pull the select cursor back so the next round sees it.
+    for (int o = 16; o; o >>= 1) min_b = min(min_b, __shfl_down_sync(0xffffffffu, min_b, o));
+    if ((threadIdx.x & 31) == 0 && min_b != INT_MAX) atomicMin(&c->cursor, max(min_b, 0));
     const unsigned long long inserted = cn.inserted, pushed = cn.pushed, reopen = cn.reopen;
     if (inserted) atomicAdd(&c->inserted, inserted);
     if (pushed) atomicAdd(&c->pushed, pushed);

@@ -28,6 +28,9 @@ class CudaEngine:
         self.torch = torch
         self.g = gpu
         self.n_parts, self.part = n_parts, part
+        # everything (kernels, NCCL, torch copies) is ordered on torch's current stream: the insert kernel must not
+        # start before the all-to-all that fills its inbox has completed
+        gpu.set_stream(torch.cuda.current_stream().cuda_stream)
         gpu.search_begin(n_parts, part, table_capacity, batch_target)
         self.xrec = gpu.xrec_stride()
         self.device = torch.device("cuda", torch.cuda.current_device())

@@ -1,0 +1,87 @@
+"""GPU parity (4): the hash-partitioned search with G logical partitions on ONE GPU (one context per partition, the
+all-to-all replaced by handing each outbox's device pointer to its owner's insert) — same optimal cost as the oracle.
+This is the N>1 data path (owner routing in the expand kernel, outbox records, insert kernel, distributed stop and
+backtrace) without needing G devices; NCCL itself is exercised by tools/multi_gpu_check.py under torchrun."""
+import numpy as np
+import pytest
+
+from conftest import CASES, KNOWN_OPT, weighted_sp_score
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+INT_MAX = 2**31 - 1
+
+
+def partitioned_search(m, seqs, parts, batch, hash_type, shift, cap=1 << 22):
+    Gs = []
+    for r in range(parts):
+        G = m.PastarGPU(seqs)
+        G.build_pair_tables()
+        G.configure_hash(hash_type, shift)
+        G.search_begin(parts, r, cap, batch)
+        Gs.append(G)
+    best, rounds, sent = INT_MAX, 0, 0
+    while True:
+        for G in Gs:
+            G.search_round(best)
+        boxes = [[G.search_outbox(d) if d != r else (0, 0) for d in range(parts)] for r, G in enumerate(Gs)]
+        for r in range(parts):
+            for d in range(parts):
+                ptr, n = boxes[r][d]
+                if n:
+                    Gs[d].search_insert_dev(ptr, n)
+                    sent += n
+        st = [G.search_status() for G in Gs]
+        mn = min(s[0] for s in st)
+        best = min(s[1] for s in st)
+        rounds += 1
+        assert rounds < 200000
+        if mn >= best or mn == INT_MAX:
+            break
+    res = {"g": best if best != INT_MAX else -1, "rounds": rounds, "sent": sent,
+           "expansions": sum(s[2]["expansions"] for s in st)}
+    # distributed backtrace: the owner of each coordinate answers
+    if best != INT_MAX:
+        n = len(seqs)
+        pos = [len(s) for s in seqs]
+        cols = []
+        while any(pos):
+            own = int(Gs[0].owner(np.array(pos, dtype=np.uint16), parts)[0])
+            hit = Gs[own].search_lookup(pos)
+            assert hit is not None, pos
+            cols.append(hit[1])
+            pos = [p - ((hit[1] >> i) & 1) for i, p in enumerate(pos)]
+        rows, at = [[] for _ in range(n)], [0] * n
+        for mask in reversed(cols):
+            for i in range(n):
+                if (mask >> i) & 1:
+                    rows[i].append(seqs[i][at[i]])
+                    at[i] += 1
+                else:
+                    rows[i].append("-")
+        res["rows"] = ["".join(r) for r in rows]
+    for G in Gs:
+        G.search_end()
+        G.close()
+    return res
+
+
+@pytest.mark.parametrize("name,parts,batch,ht,sh", [
+    ("PF08184", 2, 64, "FZORDER", 3), ("test2", 2, 256, "FSUM", 1), ("fam5x60", 2, 1024, "FZORDER", 2),
+    ("fam5x60", 3, 64, "FZORDER", 0), ("fam8x20", 4, 4096, "PZORDER", 1), ("fam4x150", 8, 4096, "FZORDER", 12),
+    ("fam6x80", 5, 512, "PSUM", 2), ("test", 4, 16, "FZORDER", 1)])
+def test_partitioned_optimal_cost(gpu_lib, name, parts, batch, ht, sh):
+    seqs = CASES[name]
+    ref = KNOWN_OPT.get(name) or O.Problem(seqs).astar(want_rows=False)["g"]
+    r = partitioned_search(gpu_lib, seqs, parts, batch, ht, sh)
+    assert r["g"] == ref, (name, parts, r)
+    w = gpu_lib.host_weights(seqs).astype(np.int32)
+    assert weighted_sp_score(seqs, w, r["rows"]) == ref
+    if parts > 1 and name != "test":
+        assert r["sent"] > 0  # successors really crossed partitions
+
+
+def test_partitioned_kinase_two_parts(gpu_lib):
+    seqs = CASES["kinase"]
+    r = partitioned_search(gpu_lib, seqs, 2, 32768, "FZORDER", 12, cap=1 << 26)
+    assert r["g"] == 421546
