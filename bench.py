@@ -27,6 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the image default prints the NCCL version)
 
 import numpy as np  # noqa: E402
 

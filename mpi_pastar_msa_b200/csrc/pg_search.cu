@@ -545,6 +545,40 @@ __device__ __forceinline__ void drain_item(const DevSearch &d, const unsigned lo
     upsert_from<KEYW>(d, key, slot, (int)(unsigned)(gf >> 32), (int)(unsigned)gf, (int)(unsigned)m, cn);
 }
 
+// Outbox space is handed out in chunks of OBOX_CHUNK records per (CTA, destination): one global atomic per chunk,
+// shared-memory atomics inside it.  state = {first record of the chunk : 40 | records used : 24}.  Records a chunk
+// does not use are marked as holes (move mask 0) and skipped by the receiver.
+constexpr unsigned OBOX_CHUNK = 256;
+template <int KEYW>
+__device__ __forceinline__ void outbox_mark_holes(const DevSearch &d, int dst, unsigned long long base, unsigned from)
+{
+    constexpr int XW = KEYW == 1 ? 3 : 4;
+    unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) + ((size_t)dst * d.outbox_cap + base) * XW;
+    for (unsigned i = from; i < OBOX_CHUNK; i++) r[(size_t)i * XW + KEYW + 1] = 0ull;
+}
+template <int KEYW>
+__device__ __forceinline__ unsigned long long outbox_reserve(const DevSearch &d, unsigned long long *s_obox, int dst, int k)
+{
+    for (;;) {
+        const unsigned long long st = atomicAdd(&s_obox[dst], (unsigned long long)k);
+        const unsigned used = (unsigned)(st & 0xffffffull);
+        const unsigned long long base = st >> 24;
+        if (used + k <= OBOX_CHUNK) return base + used;
+        if (used <= OBOX_CHUNK) { // first to run over the chunk: close it and open the next one
+            if (used < OBOX_CHUNK) outbox_mark_holes<KEYW>(d, dst, base, used);
+            unsigned long long nb = atomicAdd(&d.outbox_count[dst], (unsigned long long)OBOX_CHUNK);
+            if (nb + OBOX_CHUNK > d.outbox_cap) {
+                d.ctrl->error = 4;
+                nb = 0; // keep writes in bounds; the run is abandoned with PG_ERR_CAPACITY
+            }
+            atomicExch(&s_obox[dst], nb << 24);
+        } else { // another warp is opening the next chunk
+            while (((*(volatile unsigned long long *)&s_obox[dst]) >> 24) == base &&
+                   ((*(volatile unsigned long long *)&s_obox[dst]) & 0xffffffull) > OBOX_CHUNK) { }
+        }
+    }
+}
+
 template <int N, int KEYW>
 __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
                                                                const __grid_constant__ OwnerArgs oa)
@@ -567,6 +601,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     __shared__ unsigned long long s_cnt[8];
     __shared__ int s_ctl[4];
     __shared__ int s_tcount;
+    __shared__ unsigned long long s_obox[64];
 
     SearchCtrl *c = d.ctrl;
     if (threadIdx.x == 0) { // one reader, so the whole CTA takes the same early exit
@@ -591,6 +626,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     if (plan_sm)
         for (int i = threadIdx.x; i < plan_n; i += blockDim.x) s_plan[i] = d.plan[i].offset;
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 64) s_obox[threadIdx.x] = (unsigned long long)OBOX_CHUNK; // no chunk yet: the first append opens one
     __syncthreads();
 
     const int grp = threadIdx.x / C::LP, sub = threadIdx.x % C::LP;
@@ -711,6 +747,9 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                         const int high = (u << C::IB) | i;
                         const int mask = (high << C::A) | sub;
                         bool v = act && mask != 0 && (interior || !(mask & ~L.alive));
+                        bool rem = false;
+                        int rown = 0;
+                        Key<KEYW> rkey = Key<KEYW>::zero();
                         lk[j] = lv[j] = 0;
                         ls[j] = 0;
                         lg[j] = 0;
@@ -742,20 +781,10 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                                         if (m < oa.nb && oa.sh[m] >= 0) w |= key.field(oa.sh[m], 1u) << m;
                                     own = w % (unsigned)d.n_parts;
                                 }
-                                if ((int)own != d.part) {
-                                    // remote successor: append {key, g, f, parenti} to the owner's outbox
-                                    const unsigned long long opos = atomicAdd(&d.outbox_count[own], 1ull);
-                                    if (opos >= d.outbox_cap) {
-                                        c->error = 4;
-                                    } else {
-                                        constexpr int XW = KEYW == 1 ? 3 : 4;
-                                        unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) + ((size_t)own * d.outbox_cap + opos) * XW;
-                                        const int f = lg[j] + vh[i] + s_hhh[high];
-                                        r[0] = key.lo;
-                                        if constexpr (KEYW == 2) r[1] = key.hi;
-                                        r[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)f;
-                                        r[KEYW + 1] = (unsigned long long)(unsigned)mask;
-                                    }
+                                if ((int)own != d.part) { // remote successor: goes to the owner's outbox below
+                                    rem = true;
+                                    rown = (int)own;
+                                    rkey = key;
                                     v = false;
                                 }
                             }
@@ -770,6 +799,28 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                                     lw[j] = ld_cg_u64(e + 2);
                                 }
                                 vmask |= 1u << j;
+                            }
+                        }
+                        if (d.n_parts > 1) { // warp-uniform: one reservation per (warp, destination) from the CTA's outbox chunks
+                            unsigned todo = __ballot_sync(0xffffffffu, rem);
+                            while (todo) {
+                                const int leader = __ffs(todo) - 1;
+                                const int dst = __shfl_sync(0xffffffffu, rown, leader);
+                                const unsigned same = __ballot_sync(0xffffffffu, rem && rown == dst);
+                                unsigned long long pos0 = 0;
+                                if (lane == leader) pos0 = outbox_reserve<KEYW>(d, s_obox, dst, __popc(same));
+                                pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+                                if (rem && rown == dst) {
+                                    constexpr int XW = KEYW == 1 ? 3 : 4;
+                                    unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) +
+                                                            ((size_t)dst * d.outbox_cap + pos0 + __popc(same & lt)) * XW;
+                                    const int f = lg[j] + vh[cb + j] + s_hhh[(u << C::IB) | (cb + j)];
+                                    r[0] = rkey.lo;
+                                    if constexpr (KEYW == 2) r[1] = rkey.hi;
+                                    r[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)f;
+                                    r[KEYW + 1] = (unsigned long long)(unsigned)mask;
+                                }
+                                todo &= ~same;
                             }
                         }
                     }
@@ -830,6 +881,15 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     // ---------------- drain what is left in the warp's queue
     if (lane < (int)(qtail - qhead)) drain_item<KEYW>(d, wq + (size_t)((qhead + lane) & (Q::CAP - 1)) * Q::IW, cn);
 
+    // ---- close the CTA's open outbox chunks
+    if (d.n_parts > 1) {
+        __syncthreads();
+        if ((int)threadIdx.x < d.n_parts) {
+            const unsigned long long st = s_obox[threadIdx.x];
+            const unsigned used = (unsigned)(st & 0xffffffull);
+            if (used < OBOX_CHUNK) outbox_mark_holes<KEYW>(d, threadIdx.x, st >> 24, used);
+        }
+    }
     // ---- counters: one atomic per CTA per counter
     {
         unsigned v[6] = {cn.expansions, cn.generated, cn.reopen, cn.inserted, cn.pushed, cn.pruned};
@@ -866,6 +926,7 @@ __global__ void insert_kernel(const __grid_constant__ DevSearch d, const unsigne
         if constexpr (KEYW == 2) key.hi = r[1];
         const unsigned long long gf = r[KEYW], pm = r[KEYW + 1];
         const int gnew = (int)(unsigned)(gf >> 32), f = (int)(unsigned)gf, mask = (int)(unsigned)pm;
+        if (mask == 0) continue; // hole left by the sender's chunked outbox reservation
         bool is_goal = key.lo == d.goal_lo;
         if constexpr (KEYW == 2) is_goal = is_goal && key.hi == d.goal_hi;
         if (is_goal) atomicMin(&c->best_goal, gnew);
@@ -1339,7 +1400,7 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     if (cfg->n_parts > 1) {
         // worst case every successor of a full batch goes to one destination
         const uint64_t S = (1ull << ctx->n) - 1;
-        s->outbox_cap = (uint64_t)(s->batch_target + UNIT) * S;
+        s->outbox_cap = (uint64_t)(s->batch_target + UNIT) * S + (uint64_t)OBOX_CHUNK * 8 * (uint64_t)ctx->sm_count;
         PG_CUDA(ctx, cudaMalloc(&s->d_outbox, (size_t)cfg->n_parts * s->outbox_cap * s->xrec));
         PG_CUDA(ctx, cudaMalloc(&s->d_outbox_count, 8 * 64));
         PG_CUDA(ctx, cudaMallocHost(&s->h_outbox_count, 8 * 64));
