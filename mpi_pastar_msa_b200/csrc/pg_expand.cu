@@ -16,54 +16,74 @@
 
 namespace {
 
+// Owner of a successor without rebuilding its Morton word.  For FZORDER / PZORDER the reference keeps
+// nb = floor(log2(size)) + 2 Morton bits starting at bit `shift`; Morton bit (shift + m) is bit
+// cb[m] of coordinate ci[m].  A successor differs from its parent by +1 on the coordinates in its mask, so per
+// parent we compute W0 (the word of the parent itself) and, per coordinate i, D[i] = the bits that flip when
+// coordinate i advances; the successor's word is W0 ^ XOR_{i in mask} D[i]  (each coordinate owns distinct bits).
 struct OwnerPlan {
-    int type, shift, size, nb;
-    int sh[8]; // key bit holding Morton bit (shift + m), or -1 when that coordinate bit is always 0
+    int type, shift, size, nb, pow2;
+    int ci[8], cb[8];
 };
 
-// packed coordinate key helpers (key_bits per coordinate, little end = sequence 0)
 template <int N>
-__device__ __forceinline__ uint32_t owner_from_pos(const OwnerPlan &op, const int (&posn)[N], int key_bits)
+struct OwnerState {
+    unsigned w0;   // z-order: Morton word of the parent; sum hashes: the parent's sum
+    unsigned d[N]; // z-order: flip masks
+};
+
+template <int N>
+__device__ __forceinline__ void owner_prepare(const OwnerPlan &op, const int (&pos)[N], OwnerState<N> &os)
 {
-    if (op.size <= 1) return 0;
-    if (op.type == PG_HASH_FSUM) {
-        unsigned s = 0;
+    os.w0 = 0;
 #pragma unroll
-        for (int i = 0; i < N; i++) s += posn[i];
-        return (s >> op.shift) % (unsigned)op.size;
+    for (int i = 0; i < N; i++) os.d[i] = 0;
+    if (op.size <= 1) return;
+    if (op.type == PG_HASH_FSUM || op.type == PG_HASH_PSUM) {
+        const int nd = op.type == PG_HASH_PSUM ? 2 : N;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (i < nd) os.w0 += (unsigned)pos[i];
+        return;
     }
-    if (op.type == PG_HASH_PSUM) return ((unsigned)(posn[0] + posn[1]) >> op.shift) % (unsigned)op.size;
-    // z-order: gather the needed Morton bits from a 128-bit packed key
-    unsigned long long lo = 0, hi = 0;
+    for (int m = 0; m < op.nb; m++) {
+        const int c = op.ci[m], b = op.cb[m];
+        if (b >= 16) continue; // Coord is uint16: higher bits are always 0
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        const int off = i * key_bits;
-        if (off < 64) {
-            lo |= (unsigned long long)posn[i] << off;
-            if (off + key_bits > 64) hi |= (unsigned long long)posn[i] >> (64 - off);
-        } else {
-            hi |= (unsigned long long)posn[i] << (off - 64);
+        for (int i = 0; i < N; i++) {
+            if (i == c) {
+                const unsigned b0 = ((unsigned)pos[i] >> b) & 1u, b1 = ((unsigned)(pos[i] + 1) >> b) & 1u;
+                os.w0 |= b0 << m;
+                os.d[i] |= (b0 ^ b1) << m;
+            }
         }
     }
-    unsigned w = 0;
-    for (int m = 0; m < op.nb; m++) {
-        const int s = op.sh[m];
-        unsigned bit = 0;
-        if (s >= 64)
-            bit = (unsigned)(hi >> (s - 64)) & 1u;
-        else if (s >= 0)
-            bit = (unsigned)(lo >> s) & 1u;
-        w |= bit << m;
+}
+
+template <int N>
+__device__ __forceinline__ uint32_t owner_of_mask(const OwnerPlan &op, const OwnerState<N> &os, int mask)
+{
+    if (op.size <= 1) return 0;
+    unsigned w;
+    if (op.type == PG_HASH_FSUM) {
+        w = (os.w0 + (unsigned)__popc(mask)) >> op.shift; // CoordHash.cpp:27-44
+    } else if (op.type == PG_HASH_PSUM) {
+        w = (os.w0 + (unsigned)__popc(mask & 3)) >> op.shift; // CoordHash.cpp:47-61
+    } else {
+        w = os.w0;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if ((mask >> i) & 1) w ^= os.d[i];
     }
-    return w % (unsigned)op.size;
+    return op.pow2 ? (w & (unsigned)(op.size - 1)) : (w % (unsigned)op.size);
 }
 
 template <int N>
 struct RecordSink {
     using C = ExpCfg<N>;
     uint32_t *out;   // this parent's first record
-    OwnerPlan op;
-    int key_bits;
+    const OwnerPlan &op;
+    const OwnerState<N> &os;
     __device__ __forceinline__ void operator()(int mask, int idx, const int (&posn)[N], int gnew, int hnew)
     {
         constexpr int SW = C::POS_WORDS + 4; // words per successor record
@@ -77,7 +97,7 @@ struct RecordSink {
         w[C::POS_WORDS + 0] = (uint32_t)(gnew + hnew); // m_f, Node.cpp:38
         w[C::POS_WORDS + 1] = (uint32_t)gnew;
         w[C::POS_WORDS + 2] = (uint32_t)mask;          // parenti, Node.cpp:244
-        w[C::POS_WORDS + 3] = owner_from_pos<N>(op, posn, key_bits);
+        w[C::POS_WORDS + 3] = owner_of_mask<N>(op, os, mask);
         uint32_t *dst = out + (size_t)idx * SW;
         if constexpr (SW % 4 == 0) {
 #pragma unroll
@@ -95,7 +115,7 @@ struct RecordSink {
 };
 
 template <int N>
-__global__ void __launch_bounds__(256) expand_batch_kernel(const __grid_constant__ DevProblem p, const uint32_t *__restrict__ parents,
+__global__ void __launch_bounds__(256, 3) expand_batch_kernel(const __grid_constant__ DevProblem p, const uint32_t *__restrict__ parents,
                                                            long long k, uint32_t *__restrict__ out, int32_t *__restrict__ counts,
                                                            const __grid_constant__ OwnerPlan op)
 {
@@ -128,7 +148,9 @@ __global__ void __launch_bounds__(256) expand_batch_kernel(const __grid_constant
         const int g = (int)__shfl_sync(gmask, myw, C::POS_WORDS + 1, C::LP);
         const int parenti = (int)__shfl_sync(gmask, myw, C::POS_WORDS + 2, C::LP);
 
-        RecordSink<N> sink{out + (size_t)pi * C::S * (C::POS_WORDS + 4), op, p.key_bits};
+        OwnerState<N> os;
+        owner_prepare<N>(op, pos, os);
+        RecordSink<N> sink{out + (size_t)pi * C::S * (C::POS_WORDS + 4), op, os};
         pg_expand_parent<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, sink);
         if (sub == 0) {
             int alive = 0;
@@ -171,14 +193,15 @@ OwnerPlan make_owner_plan(const pg_ctx *ctx, int size)
     OwnerPlan op;
     op.type = ctx->dp.hash_type;
     op.shift = ctx->dp.hash_shift;
-    op.size = size;
-    op.nb = ilog2(size < 1 ? 1 : size) + 2;
+    op.size = size < 1 ? 1 : size;
+    op.pow2 = (op.size & (op.size - 1)) == 0;
+    op.nb = ilog2(op.size) + 2;
     if (op.nb > 8) op.nb = 8;
     const int nd = op.type == PG_HASH_PZORDER ? 2 : ctx->n;
     for (int m = 0; m < 8; m++) {
         const int q = op.shift + m;
-        const int coord = q % nd, bit = q / nd;
-        op.sh[m] = bit < ctx->dp.key_bits ? coord * ctx->dp.key_bits + bit : -1;
+        op.ci[m] = q % nd;
+        op.cb[m] = q / nd;
     }
     return op;
 }
