@@ -24,27 +24,31 @@
 //
 // Bound: integer ALU / dependency latency (min-plus; no tensor-core shape).
 // Bytes: one cell written once (4 B, or 2 B when 30*(L1+L2) < 65536).
+#include <algorithm>
+
 #include "pg_internal.cuh"
 
 namespace {
 
 constexpr int DP_RING = 256;  // ring entries per warp (power of two)
 constexpr int DP_CHUNK = 8;   // consumer fetch / producer publish granularity (steps)
+constexpr int DP_R = 8;       // rows per lane: a warp's band is 32 * DP_R rows
+constexpr int DP_MAXW = 4;    // warps per CTA: one per SM sub-partition, one 32*DP_R x 32 staging tile each
 
 enum { NoGap = 0, GapX = 1, GapY = 2 };
 
-struct DpShared {
-    int32_t cost[90 * 90];
-};
-
-template <typename TC>
-__global__ void __launch_bounds__(1024, 1) pair_dp_kernel(const __grid_constant__ DevProblem p, int warps)
+// AFFINE = false is the reference's actual cost model (Cost.h:13: GapOpen == GapExtension): the direction state
+// cannot change any value, so a cell is min3(below + gap, right + gap, diag + cost) - two dependent integer ops.
+// AFFINE = true carries the direction of the winning move (PairAlign.cpp:96-134) for open != extension.
+template <typename TC, bool AFFINE>
+__global__ void __launch_bounds__(32 * DP_MAXW, 1) pair_dp_kernel(const __grid_constant__ DevProblem p, int warps)
 {
+    constexpr int R = DP_R, BAND = 32 * DP_R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *s_cost = reinterpret_cast<int32_t *>(smem_raw);
     volatile int32_t *s_ring = reinterpret_cast<volatile int32_t *>(s_cost + 90 * 90);
     int32_t *s_tile = const_cast<int32_t *>(s_ring) + warps * DP_RING;
-    volatile unsigned *s_prod = reinterpret_cast<volatile unsigned *>(s_tile + warps * 32 * 33);
+    volatile unsigned *s_prod = reinterpret_cast<volatile unsigned *>(s_tile + warps * BAND * 33);
     volatile unsigned *s_cons = s_prod + warps;
 
     const int pair = blockIdx.x;
@@ -56,7 +60,11 @@ __global__ void __launch_bounds__(1024, 1) pair_dp_kernel(const __grid_constant_
     const uint8_t *s2 = p.seq[sb];
     const int open = p.gap_open, ext = p.gap_ext;
 
-    for (int i = threadIdx.x; i < 90 * 90; i += blockDim.x) s_cost[i] = p.cost[i];
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(p.cost);
+        int4 *dst = reinterpret_cast<int4 *>(s_cost);
+        for (int i = threadIdx.x; i < 90 * 90 / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
     if (threadIdx.x < warps) {
         s_prod[threadIdx.x] = 0;
         s_cons[threadIdx.x] = 0;
@@ -67,28 +75,36 @@ __global__ void __launch_bounds__(1024, 1) pair_dp_kernel(const __grid_constant_
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nbands = (L1 + 31) >> 5;
+    const int nbands = (L1 + BAND - 1) / BAND;
     if (L2 == 0) return;
-    int32_t *tile = s_tile + warp * 32 * 33;
+    int32_t *tile = s_tile + warp * BAND * 33;
     volatile int32_t *ring_out = s_ring + warp * DP_RING;
     const int pwarp = (warp + warps - 1) % warps;
     volatile int32_t *ring_in = s_ring + pwarp * DP_RING;
 
     for (int band = warp; band < nbands; band += warps) {
-        const int r = L1 - 1 - (band * 32 + lane); // my row; lane 0 is the bottom row of the band
-        const bool active = r >= 0;
-        const int32_t *costrow = s_cost + (active ? (int)s1[r] : 0) * 90;
-        int right_v = open + (L1 - 1 - r) * ext; // M[r][L2]
-        int right_d = GapX;
-        int diag_v = (r + 1 == L1) ? 0 : open + (L1 - 2 - r) * ext; // M[r+1][L2]
-        int my_pk = 0;
+        // lane l owns rows r0, r0-1, ..., r0-(R-1); k = 0 is the lowest of them, lane 0 / k 0 the bottom row of the band
+        const int r0 = L1 - 1 - (band * BAND + lane * R);
+        const int32_t *costrow[R];
+        int right_v[R], right_d[R], cst[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int r = r0 - k;
+            costrow[k] = s_cost + (r >= 0 ? (int)s1[r] : 0) * 90;
+            right_v[k] = open + (L1 - 1 - r) * ext; // M[r][L2]
+            right_d[k] = GapX;
+            cst[k] = costrow[k][s2[L2 - 1]];
+        }
+        int diag0 = (r0 + 1 == L1) ? 0 : open + (L1 - 2 - r0) * ext; // M[r0+1][L2]
+        int top_pk = 0;
         const unsigned in_base = band > 0 ? (unsigned)((band - 1) / warps) * (unsigned)L2 : 0u;
         const unsigned out_base = (unsigned)(band / warps) * (unsigned)L2;
         const bool has_consumer = band + 1 < nbands;
         const int nsteps = L2 + 31;
+        const int rows_here = min(BAND, L1 - band * BAND); // rows of this band that exist
         int nb = 0;
         int last_flush = -1;
-        int cnext = active ? costrow[s2[L2 - 1]] : 0;
+        int bnext = L2 >= 2 ? (int)s2[L2 - 2] : 0;
 
         for (int s = 0; s < nsteps; s++) {
             if ((s & (DP_CHUNK - 1)) == 0) {
@@ -113,36 +129,52 @@ __global__ void __launch_bounds__(1024, 1) pair_dp_kernel(const __grid_constant_
                     }
                 }
             }
-            const int k = s - lane;
-            int down_pk = __shfl_up_sync(0xffffffffu, my_pk, 1);
-            const int below = __shfl_sync(0xffffffffu, nb, s & (DP_CHUNK - 1));
-            if (lane == 0) down_pk = below;
-            if (active && k >= 0 && k < L2) {
-                const int j = L2 - 1 - k;
-                const int c = cnext;
-                if (j > 0) cnext = costrow[s2[j - 1]];
-                const int down_v = down_pk >> 2, down_d = down_pk & 3;
-                const int c0 = down_v + (down_d == GapX ? ext : open);
-                const int c1 = right_v + (right_d == GapY ? ext : open);
-                int m, d;
-                if (c0 < c1) {
-                    m = c0;
-                    d = GapX;
-                } else {
-                    m = c1;
-                    d = GapY;
+            const int kc = s - lane; // my column counter: column L2-1-kc
+            int below_pk = __shfl_up_sync(0xffffffffu, top_pk, 1);
+            const int below0 = __shfl_sync(0xffffffffu, nb, s & (DP_CHUNK - 1));
+            if (lane == 0) below_pk = below0;
+            if (kc >= 0 && kc < L2) {
+                const int j = L2 - 1 - kc;
+                const int bcur = bnext;               // residue of column j-1, loaded one step ahead
+                bnext = j > 1 ? (int)s2[j - 2] : 0;
+                int below_v = below_pk >> 2, below_d = below_pk & 3;
+                int dg = diag0;
+                diag0 = below_v;
+                int32_t *trow = tile + (lane * R) * 33 + (kc & 31);
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    const int old_v = right_v[k];
+                    int m;
+                    if (AFFINE) {
+                        const int old_d = right_d[k];
+                        const int c0 = below_v + (below_d == GapX ? ext : open);
+                        const int c1 = old_v + (old_d == GapY ? ext : open);
+                        int d;
+                        if (c0 < c1) {
+                            m = c0;
+                            d = GapX;
+                        } else {
+                            m = c1;
+                            d = GapY;
+                        }
+                        const int c2 = dg + cst[k];
+                        if (c2 < m) {
+                            m = c2;
+                            d = NoGap;
+                        }
+                        right_d[k] = d;
+                        below_d = d;
+                    } else {
+                        m = __vimin3_s32(below_v + open, old_v + open, dg + cst[k]);
+                    }
+                    cst[k] = costrow[k][bcur]; // next column's substitution cost, off the critical path
+                    right_v[k] = m;
+                    trow[k * 33] = m;
+                    dg = old_v;
+                    below_v = m;
                 }
-                const int c2 = diag_v + c;
-                if (c2 < m) {
-                    m = c2;
-                    d = NoGap;
-                }
-                diag_v = down_v;
-                right_v = m;
-                right_d = d;
-                my_pk = (m << 2) | d;
-                tile[lane * 33 + (k & 31)] = m;
-                if (lane == 31 && has_consumer) ring_out[(out_base + k) & (DP_RING - 1)] = my_pk;
+                top_pk = (below_v << 2) | below_d;
+                if (lane == 31 && has_consumer) ring_out[(out_base + kc) & (DP_RING - 1)] = top_pk;
             }
             // --- publish the top row's progress
             if (has_consumer && ((s & (DP_CHUNK - 1)) == DP_CHUNK - 1 || s == nsteps - 1)) {
@@ -150,14 +182,22 @@ __global__ void __launch_bounds__(1024, 1) pair_dp_kernel(const __grid_constant_
                 const int k31 = s - 31;
                 if (lane == 31 && k31 >= 0) s_prod[warp] = out_base + (unsigned)min(k31 + 1, L2);
             }
-            // --- write the staged tile out as row segments
+            // --- write the staged tile out as row segments of up to 32 cells
             if ((s & 31) == 31 || s == nsteps - 1) {
                 __syncwarp();
-                for (int rr = 0; rr < 32; rr++) {
-                    const int row = L1 - 1 - (band * 32 + rr);
-                    if (row < 0) break;
-                    const int kk = last_flush + 1 - rr + lane;
-                    if (kk >= 0 && kk <= s - rr && kk < L2) M[(size_t)row * cols + (L2 - 1 - kk)] = (TC)tile[rr * 33 + (kk & 31)];
+                TC *rowp = M + (size_t)(L1 - 1 - band * BAND) * cols + (L2 - 1); // row of rr = 0, column of kk = 0
+                const int32_t *trd = tile;
+                int rr = 0;
+                for (int ln = 0; ln < 32 && rr < rows_here; ln++) {
+                    const int kk = last_flush + 1 - ln + lane;
+                    const bool ok = kk >= 0 && kk <= s - ln && kk < L2;
+                    const int slot = kk & 31;
+#pragma unroll
+                    for (int k = 0; k < R; k++, rr++) {
+                        if (ok && rr < rows_here) rowp[-kk] = (TC)trd[slot];
+                        rowp -= cols;
+                        trd += 33;
+                    }
                 }
                 last_flush = s;
                 __syncwarp();
@@ -171,23 +211,31 @@ __global__ void __launch_bounds__(1024, 1) pair_dp_kernel(const __grid_constant_
 int pg_launch_pair_dp(pg_ctx *ctx, float *kernel_ms)
 {
     int max_bands = 1;
-    for (const PairGeom &g : ctx->pairs) max_bands = std::max(max_bands, (g.rows - 1 + 31) / 32);
-    const int warps = std::min(32, max_bands);
-    const size_t smem = sizeof(int32_t) * 90 * 90 + (size_t)warps * DP_RING * 4 + (size_t)warps * 32 * 33 * 4 + (size_t)warps * 8;
+    for (const PairGeom &g : ctx->pairs) max_bands = std::max(max_bands, (g.rows - 1 + 32 * DP_R - 1) / (32 * DP_R));
+    const int warps = std::min(DP_MAXW, max_bands);
+    const size_t smem = sizeof(int32_t) * 90 * 90 + (size_t)warps * DP_RING * 4 + (size_t)warps * 32 * DP_R * 33 * 4 + (size_t)warps * 8;
+    const bool affine = ctx->dp.gap_open != ctx->dp.gap_ext;
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<ctx->npairs, warps * 32, smem, ctx->stream>>>(ctx->dp, warps);
+        return cudaGetLastError();
+    };
     cudaEvent_t e0, e1;
     PG_CUDA(ctx, cudaEventCreate(&e0));
     PG_CUDA(ctx, cudaEventCreate(&e1));
-    if (ctx->dp.cell16) {
-        PG_CUDA(ctx, cudaFuncSetAttribute(pair_dp_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else {
-        PG_CUDA(ctx, cudaFuncSetAttribute(pair_dp_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
     PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    if (ctx->dp.cell16)
-        pair_dp_kernel<uint16_t><<<ctx->npairs, warps * 32, smem, ctx->stream>>>(ctx->dp, warps);
-    else
-        pair_dp_kernel<int32_t><<<ctx->npairs, warps * 32, smem, ctx->stream>>>(ctx->dp, warps);
-    PG_CUDA(ctx, cudaGetLastError());
+    if (ctx->dp.cell16) {
+        if (affine)
+            PG_CUDA(ctx, launch(pair_dp_kernel<uint16_t, true>));
+        else
+            PG_CUDA(ctx, launch(pair_dp_kernel<uint16_t, false>));
+    } else {
+        if (affine)
+            PG_CUDA(ctx, launch(pair_dp_kernel<int32_t, true>));
+        else
+            PG_CUDA(ctx, launch(pair_dp_kernel<int32_t, false>));
+    }
     PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
