@@ -123,7 +123,7 @@ typedef struct {
     int64_t batch_target;   /* frontier nodes popped per round (whole f-buckets, at least one); 0 = auto */
     int64_t max_expansions; /* > 0: stop after this many expansions (budgeted run, not optimal)  */
     int32_t rounds_per_sync;/* rounds launched between host checks; 0 = auto                     */
-    int32_t reserved;
+    int32_t reserved;       /* 1 = P2P mode: see pg_search_set_peers                              */
 } pg_search_config;
 
 typedef struct {
@@ -167,6 +167,17 @@ int pg_search_rounds(pg_ctx *ctx, int32_t rounds, int32_t f_limit);
 int pg_search_profile(pg_ctx *ctx, int enable);
 /* Device pointer + record count of the outbox for partition dst (valid until the next round). */
 int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count);
+/* P2P mode (the fused compute + exchange variant): give every partition's inbox base as seen from THIS device
+ * (peer-mapped over NVLink, e.g. torch symmetric memory / CUDA IPC).  The expand kernel then stores remote
+ * successors straight into region [part] of inbox[dst] (pg_search_outbox_capacity() records of pg_xrec_stride()
+ * bytes per region) while it computes; only the per-destination counts still travel by collective.  Request it
+ * with pg_search_config.reserved = 1 in pg_search_begin (no local outbox is allocated). */
+int pg_search_set_peers(pg_ctx *ctx, void *const *peer_inbox, int n);
+int64_t pg_search_outbox_capacity(const pg_ctx *ctx);
+/* device pointer to the per-destination record counts of the last round (uint64[64]) */
+int pg_search_outbox_counts_dev(pg_ctx *ctx, void **d_counts);
+/* insert n segments: segment i = counts[i] records at base + i*stride_bytes (one host sync at the end) */
+int pg_search_insert_segments_dev(pg_ctx *ctx, const void *base, int64_t stride_bytes, const int64_t *counts, int n);
 /* Dedupe + push records received from other partitions (device pointer). */
 int pg_search_insert_dev(pg_ctx *ctx, const void *d_records, int64_t count);
 /* Local lower bound of open f (INT32_MAX when empty), best goal g seen here

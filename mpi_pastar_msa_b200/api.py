@@ -84,6 +84,10 @@ def load_library():
         "pg_search_round": ([vp, C.c_int32], i32),
         "pg_search_outbox": ([vp, i32, C.POINTER(vp), C.POINTER(i64)], i32),
         "pg_search_insert_dev": ([vp, vp, i64], i32),
+        "pg_search_set_peers": ([vp, C.POINTER(vp), i32], i32),
+        "pg_search_outbox_capacity": ([vp], i64),
+        "pg_search_outbox_counts_dev": ([vp, C.POINTER(vp)], i32),
+        "pg_search_insert_segments_dev": ([vp, vp, i64, C.POINTER(i64), i32], i32),
         "pg_search_status": ([vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(Result)], i32),
         "pg_search_lookup": ([vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)], i32),
         "pg_search_end": ([vp], i32),
@@ -97,7 +101,8 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
+EXPORTS = ["pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+           "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
            "pg_search_outbox", "pg_search_insert_dev", "pg_search_status", "pg_search_lookup", "pg_search_end",
@@ -284,9 +289,25 @@ class PastarGPU:
         return d
 
     # step-wise (multi-GPU drivers)
-    def search_begin(self, n_parts=1, part=0, table_capacity=0, batch_target=0):
-        cfg = SearchConfig(n_parts, part, table_capacity, batch_target, 0, 0, 0)
+    def search_begin(self, n_parts=1, part=0, table_capacity=0, batch_target=0, p2p=False):
+        cfg = SearchConfig(n_parts, part, table_capacity, batch_target, 0, 0, 1 if p2p else 0)
         self._ck(self.L.pg_search_begin(self.h, C.byref(cfg)))
+
+    def search_set_peers(self, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._ck(self.L.pg_search_set_peers(self.h, arr, len(ptrs)))
+
+    def search_outbox_capacity(self):
+        return int(self.L.pg_search_outbox_capacity(self.h))
+
+    def search_outbox_counts_dev(self):
+        p = C.c_void_p()
+        self._ck(self.L.pg_search_outbox_counts_dev(self.h, C.byref(p)))
+        return p.value
+
+    def search_insert_segments_dev(self, base, stride_bytes, counts):
+        arr = (C.c_int64 * len(counts))(*[int(c) for c in counts])
+        self._ck(self.L.pg_search_insert_segments_dev(self.h, base, stride_bytes, arr, len(counts)))
 
     def search_round(self, f_limit=2**31 - 1):
         self._ck(self.L.pg_search_round(self.h, f_limit))

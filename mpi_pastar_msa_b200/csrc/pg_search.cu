@@ -79,6 +79,8 @@ struct SearchState {
     unsigned long long *d_outbox_count = nullptr;
     unsigned long long *h_outbox_count = nullptr;
     uint64_t outbox_cap = 0; // records per destination
+    void *peer_inbox[16] = {nullptr};
+    bool p2p = false;
     int xrec = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-launch timing: event triples (before select, between, after expand), harvested at every sync
@@ -185,6 +187,9 @@ struct DevSearch {
     char *outbox;
     unsigned long long *outbox_count;
     unsigned long long outbox_cap;
+    // P2P mode: base of every partition's (peer-mapped) inbox; this partition writes region [part] of inbox[dst]
+    char *peer_inbox[16];
+    int p2p;
 };
 
 struct Counters { // per thread, flushed once per kernel
@@ -549,11 +554,20 @@ __device__ __forceinline__ void drain_item(const DevSearch &d, const unsigned lo
 // shared-memory atomics inside it.  state = {first record of the chunk : 40 | records used : 24}.  Records a chunk
 // does not use are marked as holes (move mask 0) and skipped by the receiver.
 constexpr unsigned OBOX_CHUNK = 256;
+// Where record `pos` for partition dst lives: the local outbox (NCCL all-to-all mode), or directly the owner's
+// peer-mapped inbox over NVLink (P2P mode): region [this partition] of inbox[dst].
+template <int KEYW>
+__device__ __forceinline__ unsigned long long *outbox_record(const DevSearch &d, int dst, unsigned long long pos)
+{
+    constexpr int XW = KEYW == 1 ? 3 : 4;
+    if (d.p2p) return reinterpret_cast<unsigned long long *>(d.peer_inbox[dst]) + ((size_t)d.part * d.outbox_cap + pos) * XW;
+    return reinterpret_cast<unsigned long long *>(d.outbox) + ((size_t)dst * d.outbox_cap + pos) * XW;
+}
 template <int KEYW>
 __device__ __forceinline__ void outbox_mark_holes(const DevSearch &d, int dst, unsigned long long base, unsigned from)
 {
     constexpr int XW = KEYW == 1 ? 3 : 4;
-    unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) + ((size_t)dst * d.outbox_cap + base) * XW;
+    unsigned long long *r = outbox_record<KEYW>(d, dst, base);
     for (unsigned i = from; i < OBOX_CHUNK; i++) r[(size_t)i * XW + KEYW + 1] = 0ull;
 }
 template <int KEYW>
@@ -811,9 +825,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                                 if (lane == leader) pos0 = outbox_reserve<KEYW>(d, s_obox, dst, __popc(same));
                                 pos0 = __shfl_sync(0xffffffffu, pos0, leader);
                                 if (rem && rown == dst) {
-                                    constexpr int XW = KEYW == 1 ? 3 : 4;
-                                    unsigned long long *r = reinterpret_cast<unsigned long long *>(d.outbox) +
-                                                            ((size_t)dst * d.outbox_cap + pos0 + __popc(same & lt)) * XW;
+                                    unsigned long long *r = outbox_record<KEYW>(d, dst, pos0 + __popc(same & lt));
                                     const int f = lg[j] + vh[cb + j] + s_hhh[(u << C::IB) | (cb + j)];
                                     r[0] = rkey.lo;
                                     if constexpr (KEYW == 2) r[1] = rkey.hi;
@@ -1152,6 +1164,8 @@ DevSearch dev_search(const pg_ctx *ctx)
     d.outbox = s->d_outbox;
     d.outbox_count = s->d_outbox_count;
     d.outbox_cap = s->outbox_cap;
+    d.p2p = s->p2p ? 1 : 0;
+    for (int i = 0; i < 16; i++) d.peer_inbox[i] = (char *)s->peer_inbox[i];
     return d;
 }
 
@@ -1401,7 +1415,8 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
         // worst case every successor of a full batch goes to one destination
         const uint64_t S = (1ull << ctx->n) - 1;
         s->outbox_cap = (uint64_t)(s->batch_target + UNIT) * S + (uint64_t)OBOX_CHUNK * 8 * (uint64_t)ctx->sm_count;
-        PG_CUDA(ctx, cudaMalloc(&s->d_outbox, (size_t)cfg->n_parts * s->outbox_cap * s->xrec));
+        if (cfg->reserved != 1) // reserved == 1: P2P mode, records go straight to the peers' inboxes (pg_search_set_peers)
+            PG_CUDA(ctx, cudaMalloc(&s->d_outbox, (size_t)cfg->n_parts * s->outbox_cap * s->xrec));
         PG_CUDA(ctx, cudaMalloc(&s->d_outbox_count, 8 * 64));
         PG_CUDA(ctx, cudaMallocHost(&s->h_outbox_count, 8 * 64));
         PG_CUDA(ctx, cudaMemsetAsync(s->d_outbox_count, 0, 8 * 64, ctx->stream));
@@ -1436,6 +1451,7 @@ extern "C" int pg_search_round(pg_ctx *ctx, int32_t f_limit)
     if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     SearchState *s = ctx->search;
+    if (s->cfg.n_parts > 1 && s->cfg.reserved == 1 && !s->p2p) return pg_fail(ctx, PG_ERR_STATE, "P2P mode requested but pg_search_set_peers has not run");
     if (s->cfg.n_parts > 1) PG_CUDA(ctx, cudaMemsetAsync(s->d_outbox_count, 0, 8 * 64, ctx->stream));
     int rc = launch_round(ctx, f_limit);
     if (rc != PG_OK) return rc;
@@ -1461,6 +1477,46 @@ extern "C" int pg_search_profile(pg_ctx *ctx, int enable)
     if (!ctx || !ctx->search) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
     ctx->search->profile = enable != 0;
     return PG_OK;
+}
+
+extern "C" int pg_search_set_peers(pg_ctx *ctx, void *const *peer_inbox, int n)
+{
+    if (!ctx || !ctx->search || !peer_inbox) return PG_ERR_ARG;
+    SearchState *s = ctx->search;
+    if (n != s->cfg.n_parts || n > 16) return pg_fail(ctx, PG_ERR_ARG, "pg_search_set_peers: one inbox base per partition, at most 16");
+    for (int i = 0; i < n; i++) s->peer_inbox[i] = peer_inbox[i];
+    s->p2p = true;
+    return PG_OK;
+}
+
+extern "C" int64_t pg_search_outbox_capacity(const pg_ctx *ctx)
+{
+    return ctx && ctx->search ? (int64_t)ctx->search->outbox_cap : 0;
+}
+
+extern "C" int pg_search_outbox_counts_dev(pg_ctx *ctx, void **d_counts)
+{
+    if (!ctx || !ctx->search || !d_counts) return PG_ERR_ARG;
+    *d_counts = ctx->search->d_outbox_count;
+    return PG_OK;
+}
+
+extern "C" int pg_search_insert_segments_dev(pg_ctx *ctx, const void *base, int64_t stride_bytes, const int64_t *counts, int n)
+{
+    if (!ctx || !ctx->search || !base || !counts || n < 0) return PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SearchState *s = ctx->search;
+    for (int i = 0; i < n; i++) {
+        if (counts[i] <= 0) continue;
+        const unsigned long long *recs = (const unsigned long long *)((const char *)base + (size_t)i * stride_bytes);
+        const long long grid = std::min<long long>((counts[i] + 255) / 256, (long long)ctx->sm_count * 8);
+        if (s->keyw == 1)
+            insert_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), recs, (long long)counts[i]);
+        else
+            insert_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), recs, (long long)counts[i]);
+        PG_CUDA(ctx, cudaGetLastError());
+    }
+    return sync_ctrl(ctx);
 }
 
 extern "C" int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count)

@@ -69,6 +69,46 @@ class CudaEngine:
         self.g.search_end()
 
 
+class CudaEngineP2P(CudaEngine):
+    """Fused expansion + exchange: the expand kernel stores remote successors straight into the owner's inbox over
+    NVLink (peer-mapped symmetric memory); only the per-destination counts travel by collective.  Replaces the
+    bulk all-to-all of CudaEngine (same records, same insert kernel)."""
+
+    def __init__(self, gpu, n_parts, part, dist, table_capacity=0, batch_target=0):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        self.torch, self.g, self.n_parts, self.part = torch, gpu, n_parts, part
+        if n_parts > 16:
+            raise ValueError("P2P mode supports up to 16 partitions")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+        gpu.search_begin(n_parts, part, table_capacity, batch_target, p2p=True)
+        self.xrec = gpu.xrec_stride()
+        self.region = gpu.search_outbox_capacity() * self.xrec          # bytes one source may write into one inbox
+        self.inbox = symm.empty(n_parts * self.region, dtype=torch.uint8, device=self.device)
+        self.hdl = symm.rendezvous(self.inbox, dist.group.WORLD)
+        gpu.search_set_peers([int(self.hdl.buffer_ptrs[r]) for r in range(n_parts)])
+        self.counts = self._wrap64(gpu.search_outbox_counts_dev(), n_parts)
+        self.bytes_sent = 0
+        dist.barrier()
+
+    def _wrap64(self, ptr, n):
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+        return self.torch.as_tensor(_Mem(), device=self.device)
+
+    def round_and_exchange(self, f_limit, dist):
+        t = self.torch
+        self.g.search_round(f_limit)                       # remote successors are already in their owners' inboxes
+        allc = t.empty(self.n_parts * self.n_parts, dtype=t.int64, device=self.device)
+        dist.all_gather_into_tensor(allc, self.counts)     # also orders every rank's stores before any insert
+        allc = allc.view(self.n_parts, self.n_parts)
+        mine = allc[:, self.part].tolist()                 # records source s wrote into my region s
+        mine[self.part] = 0
+        self.bytes_sent += int(allc[self.part].sum().item()) * self.xrec
+        self.g.search_insert_segments_dev(self.inbox.data_ptr(), self.region, mine)
+
+
 class PartitionedSearch:
     """The per-rank loop.  `dist` is torch.distributed (initialised by the caller), engine as above."""
 
@@ -104,15 +144,23 @@ class PartitionedSearch:
     def step(self, f_limit=INT_MAX):
         """One round; returns (global min open f, global best goal g, global expansions)."""
         t, dist = self.torch, self.dist
-        outboxes = self.e.round(f_limit)
-        self.e.insert(self.exchange(outboxes))
+        if hasattr(self.e, "round_and_exchange"):
+            self.e.round_and_exchange(f_limit, dist)
+            self.bytes_sent = self.e.bytes_sent
+        else:
+            outboxes = self.e.round(f_limit)
+            self.e.insert(self.exchange(outboxes))
         mn, best, cnt = self.e.status()
-        red = t.tensor([mn, best], dtype=t.int64, device=self._dev())
-        dist.all_reduce(red, op=dist.ReduceOp.MIN)
-        tot = t.tensor([cnt["expansions"], cnt["generated"], cnt["pops"]], dtype=t.int64, device=self._dev())
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        # one small collective for the stop test and the counters: min over ranks of {min open f, best goal g}
+        # (PAStar.cpp:502-519) and the sums
+        mine = t.tensor([mn, best, cnt["expansions"], cnt["generated"], cnt["pops"]], dtype=t.int64, device=self._dev())
+        allv = t.empty(self.world * 5, dtype=t.int64, device=self._dev())
+        dist.all_gather_into_tensor(allv, mine)
+        allv = allv.view(self.world, 5)
+        mins = allv[:, :2].min(dim=0).values.tolist()
+        tot = allv[:, 2:].sum(dim=0).tolist()
         self.rounds += 1
-        return int(red[0]), int(red[1]), [int(x) for x in tot]
+        return int(mins[0]), int(mins[1]), [int(x) for x in tot]
 
     def run(self):
         """Search to the optimality-preserving stop (or the expansion budget).  Returns a dict on every rank."""

@@ -10,5 +10,6 @@ mx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 seqs = CASES["kinase"] if which == "kinase" else S7()
 with m.PastarGPU(seqs) as G:
     G.build_pair_tables()
-    r = G.search(want_rows=False, table_capacity=1 << 27, batch_target=bt, max_expansions=mx)
+    cap = int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 27
+    r = G.search(want_rows=False, table_capacity=cap, batch_target=bt, max_expansions=mx)
     print(r)
