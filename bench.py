@@ -198,11 +198,16 @@ def run_ours(args, rank, world):
         max_ms = ms
         G.search_end()
     else:
-        from mpi_pastar_msa_b200.dist import CudaEngine, PartitionedSearch
+        from mpi_pastar_msa_b200.dist import CudaEngine, CudaEngineP2P, PartitionedSearch
         G.configure_hash("FZORDER", 12)
-        eng = CudaEngine(G, world, rank, cap, batch)
+        try:  # fused expansion + exchange over peer-mapped inboxes; NCCL all-to-all if symmetric memory is unavailable
+            eng = CudaEngineP2P(G, world, rank, dist, cap, batch)
+            extra["exchange"] = "p2p stores into peer-mapped inboxes (NVLink), counts by all_gather"
+        except Exception as ex:
+            eng = CudaEngine(G, world, rank, cap, batch)
+            extra["exchange"] = "nccl all_to_all_single (p2p unavailable: %r)" % (ex,)
         drv = PartitionedSearch(eng, dist, seqs, lambda pos: int(G.owner(np.array(pos, dtype=np.uint16), world)[0]))
-        launches_per_step = 4  # select + fused expand + insert + status select
+        launches_per_step = 3 + (world - 1)  # select + fused expand + one insert per source + status select
         ramp = 0
         while True:
             _, _, tot0 = drv.step()
@@ -289,6 +294,14 @@ def run_ours(args, rank, world):
         extra["expand_only"] = {"kernel": "expand_batch_kernel<7>", "expansions_per_sec": Kx / (xms * 1e-3), "successors_per_sec": Kx * S / (xms * 1e-3),
                                 "bytes_per_expansion": bexp, "achieved_gbs": Kx * bexp / (xms * 1e-3) / 1e9,
                                 "frac_of_hbm": Kx * bexp / (xms * 1e-3) / 1e9 / hbm, "output_mb": Kx * S * sst / 1e6}
+        try:
+            gl = m.bench_random_gather(cap * 16, local)
+            probes = d["probed"] / (expand_ms * 1e-3)
+            extra["gather_roofline"] = {"what": "random 16 B loads/s over a table of the bench's size, 8 in flight per thread (pg_bench_random_gather)",
+                                        "table_gib": cap * 16 / 2**30, "measured_loads_per_sec": gl, "kernel_probes_per_sec": probes,
+                                        "frac": probes / gl}
+        except Exception as ex:
+            extra["gather_roofline"] = {"error": repr(ex)}
         extra["pair_dp"] = {"kernel": "pair_dp_kernel", "cells": cells, "ms": dp_ms, "gcups": cells / (dp_ms * 1e-3) / 1e9}
         del d_out
 

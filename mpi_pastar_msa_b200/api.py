@@ -84,6 +84,7 @@ def load_library():
         "pg_search_round": ([vp, C.c_int32], i32),
         "pg_search_outbox": ([vp, i32, C.POINTER(vp), C.POINTER(i64)], i32),
         "pg_search_insert_dev": ([vp, vp, i64], i32),
+        "pg_bench_random_gather": ([i32, i64, C.POINTER(C.c_double)], i32),
         "pg_search_set_peers": ([vp, C.POINTER(vp), i32], i32),
         "pg_search_outbox_capacity": ([vp], i64),
         "pg_search_outbox_counts_dev": ([vp, C.POINTER(vp)], i32),
@@ -101,7 +102,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -148,6 +149,15 @@ def default_cost_table():
     out = np.zeros(8100, dtype=np.int32)
     load_library().pg_default_cost_table(out.ctypes.data)
     return out.reshape(90, 90)
+
+
+def bench_random_gather(nbytes, device=-1):
+    """Random 16-byte loads/s over an nbytes table: the measured ceiling for the dedupe probe."""
+    out = C.c_double()
+    rc = load_library().pg_bench_random_gather(device, int(nbytes), C.byref(out))
+    if rc:
+        raise PastarError(rc, "pg_bench_random_gather")
+    return out.value
 
 
 def host_weights(seqs):

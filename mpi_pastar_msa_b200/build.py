@@ -21,7 +21,7 @@ CXX = os.environ.get("CXX", "g++")
 CU_SOURCES = ["pg_api.cu", "pg_pairdp.cu", "pg_expand.cu", "pg_search.cu"]
 HOST_SOURCES = ["host/pg_host_weights.cpp"]
 CLI_SOURCES = ["host/pastar_main.cpp"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+NVCC_FLAGS = (["-DPG_PHASE_TIMING"] if os.environ.get("PG_PHASE_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 # -ffp-contract=off: the host weight routine must not fuse multiply-adds (float-order exact vs the reference)
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]

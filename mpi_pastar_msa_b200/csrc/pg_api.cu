@@ -14,6 +14,72 @@ int pg_fail(pg_ctx *ctx, int code, const std::string &msg)
 
 extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
 
+// ---- measured ceiling of the closed/open-table probe: random 16-byte loads over `bytes` of HBM, 8 in flight per thread
+namespace {
+__global__ void gather_probe_kernel(const unsigned long long *tab, unsigned long long mask, int iters, unsigned long long *out)
+{
+    unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long acc = 0, seed = tid * 0x1234567ull + 1;
+    for (int it = 0; it < iters; it++) {
+        unsigned long long a[8], b[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            seed = (seed + j) * 0x9E3779B97F4A7C15ull;
+            seed ^= seed >> 32;
+            seed *= 0xD6E8FEB86659FD93ull;
+            seed ^= seed >> 29;
+            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a[j]), "=l"(b[j]) : "l"(tab + 2 * (seed & mask)) : "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += a[j] ^ b[j];
+    }
+    if (acc == 0x1234) out[0] = acc;
+}
+} // namespace
+
+extern "C" int pg_bench_random_gather(int device, int64_t bytes, double *loads_per_sec)
+{
+    if (!loads_per_sec || bytes < (1 << 20)) return PG_ERR_ARG;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PG_ERR_CUDA;
+    unsigned long long entries = 1;
+    while (entries * 2 * 16 <= (unsigned long long)bytes) entries *= 2;
+    unsigned long long *tab = nullptr, *out = nullptr;
+    if (cudaMalloc(&tab, entries * 16) != cudaSuccess) return PG_ERR_CUDA;
+    if (cudaMalloc(&out, 64) != cudaSuccess) {
+        cudaFree(tab);
+        return PG_ERR_CUDA;
+    }
+    cudaMemset(tab, 0, entries * 16);
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaGetDeviceProperties(&prop, dev);
+    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 64;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    gather_probe_kernel<<<blocks, threads>>>(tab, entries - 1, iters, out);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0);
+        gather_probe_kernel<<<blocks, threads>>>(tab, entries - 1, iters, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(tab);
+    cudaFree(out);
+    if (err != cudaSuccess) return PG_ERR_CUDA;
+    *loads_per_sec = (double)blocks * threads * iters * 8 / (best * 1e-3);
+    return PG_OK;
+}
+
 extern "C" const char *pg_last_error(const pg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int pg_stage(pg_ctx *ctx, int which, size_t bytes, void **out)

@@ -50,6 +50,7 @@ struct SearchCtrl {          // lives in device memory; mirrored to pinned host 
     uint32_t chunk_bump;     // next free chunk
     uint32_t pad0;
     unsigned long long pops, expansions, generated, reopen, inserted, pushed, pruned, table_used;
+    unsigned long long phase[8]; // PG_PHASE_TIMING builds: warp-cycles per phase of the expand kernel
 };
 
 struct SearchState;

@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -149,6 +150,36 @@ struct Key<2> {
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Table placement.  A random 16-byte probe costs a whole 128-byte line of HBM traffic (measured: 36.5 G random lines/s
+// however many of a line's 8 entries are read, tools/microbench2.cu), so the table is laid out so that the successors of
+// one parent share lines: the home LINE is hashed from the key with the lowest bit of its first LB coordinates
+// cleared, and those LB bits select the entry inside the line (LB = 3: 8 x 16 B entries; LB = 2: 4 x 32 B).  The
+// 2^LB successors that differ only in whether those coordinates advance land in one line when the parent's coordinates
+// are even (1.5^LB lines on average instead of 2^LB), and neighbouring parents share lines too.  Collisions probe the
+// same entry position of the following lines (stride 2^LB slots), so the layout is kept.
+// ---------------------------------------------------------------------------------------------
+template <int KEYW>
+__device__ __forceinline__ unsigned long long home_slot(const Key<KEYW> &key, int kb, unsigned long long cap_mask)
+{
+    constexpr int LB = KEYW == 1 ? 3 : 2;
+    unsigned long long low = 0, clr = 0;
+#pragma unroll
+    for (int i = 0; i < LB; i++) {
+        low |= ((key.lo >> (i * kb)) & 1ull) << i; // LB * kb < 64 always (kb <= 16)
+        clr |= 1ull << (i * kb);
+    }
+    Key<KEYW> blk = key;
+    blk.lo &= ~clr;
+    return ((blk.hash() << LB) | low) & cap_mask;
+}
+template <int KEYW>
+__device__ __forceinline__ unsigned long long next_slot(unsigned long long slot, unsigned long long cap_mask)
+{
+    return (slot + (KEYW == 1 ? 8ull : 4ull)) & cap_mask;
+}
+
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p)
 {
     unsigned long long v;
@@ -173,6 +204,7 @@ __device__ __forceinline__ void cas128(unsigned long long *addr, unsigned long l
 struct DevSearch {
     unsigned long long *table;
     unsigned long long cap_mask;
+    int kb; // bits per coordinate in the packed key
     unsigned long long *buckets;
     uint32_t *tail;
     uint32_t *hint; // per bucket: log2 units of the largest chunk it ever had
@@ -202,9 +234,9 @@ template <int KEYW>
 __device__ __forceinline__ unsigned long long table_slot(const DevSearch &d, const Key<KEYW> &key, unsigned long long &val, bool &fresh)
 {
     constexpr int ES = KEYW == 1 ? 2 : 4;
-    unsigned long long slot = key.hash() & d.cap_mask;
+    unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
     fresh = false;
-    for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+    for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
         unsigned long long *e = d.table + slot * ES;
         if constexpr (KEYW == 1) {
             unsigned long long k, v;
@@ -455,6 +487,12 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, lon
 //                    is appended to a per-warp shared-memory queue and
 //            drain:  executed 32 items at a time with all lanes active (CAS on key / value, push to the f bucket),
 //                    so the rare slow path does not serialise the warp.
+#ifdef PG_PHASE_TIMING
+#define PH_MARK(idx) do { long long t__ = clock64(); ph[idx] += t__ - ph_t; ph_t = t__; } while (0)
+#else
+#define PH_MARK(idx) do { } while (0)
+#endif
+
 struct OwnerArgs {
     int type, shift, nb;
     int sh[8];
@@ -474,7 +512,7 @@ __device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> 
     constexpr int ES = KEYW == 1 ? 2 : 4;
     unsigned long long val = 0;
     bool found = false;
-    for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+    for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
         unsigned long long *e = d.table + slot * ES;
         if constexpr (KEYW == 1) {
             unsigned long long k, v;
@@ -652,6 +690,10 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     const int *s_hhh = s_hhg + C::H;
     unsigned long long *wq = s_queue + (size_t)warp * Q::CAP * Q::IW;
     unsigned qhead = 0, qtail = 0; // warp-uniform ring indices
+#ifdef PG_PHASE_TIMING
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_t = clock64();
+#endif
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     const unsigned fmask = (1u << p.key_bits) - 1u;
     const int full = (1 << N) - 1;
@@ -659,6 +701,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     for (int tbase = blockIdx.x * 256; tbase < batch_n; tbase += gridDim.x * 256) {
         if (threadIdx.x == 0) s_tcount = 0;
         __syncthreads();
+        PH_MARK(0); // barrier / tile turnover
         // ---------------- stage 0: claim
         {
             const int bi = tbase + threadIdx.x;
@@ -703,7 +746,9 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                 s_tval[idx] = val;
             }
         }
+        PH_MARK(1); // stage 0 claim
         __syncthreads();
+        PH_MARK(0);
         const int nlive = s_tcount;
         const int iters = (nlive + GROUPS - 1) / GROUPS;
 
@@ -738,6 +783,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                     pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
                 }
             }
+            PH_MARK(2); // prepare (LUT gathers, HH, B/E)
             Key<KEYW> klow = pkey;
 #pragma unroll
             for (int i = 0; i < C::A; i++)
@@ -803,7 +849,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                                 }
                             }
                             if (v) {
-                                const unsigned long long slot = key.hash() & d.cap_mask;
+                                const unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
                                 ls[j] = (uint32_t)slot;
                                 const unsigned long long *e = d.table + slot * (KEYW == 1 ? 2 : 4);
                                 if constexpr (KEYW == 1) {
@@ -836,6 +882,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                             }
                         }
                     }
+                    PH_MARK(3); // pass 1: issue probes (+ remote appends)
                     // ---- pass 2: classify; queue what needs an atomic
 #pragma unroll
                     for (int j = 0; j < PF; j++) {
@@ -853,7 +900,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                                     slow = (unsigned)lg[j] < g_old; // better g: needs the CAS
                                 } else {
                                     slow = true; // empty slot or collision
-                                    if (lk[j] != 0) start = (start + 1) & d.cap_mask;
+                                    if (lk[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
                                 }
                             } else {
                                 if (lk[j] == key.lo && lv[j] == (key.hi | (1ull << 63))) {
@@ -861,7 +908,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                                     slow = (unsigned)lg[j] < g_old;
                                 } else {
                                     slow = true;
-                                    if (lk[j] != 0 || lv[j] != 0) start = (start + 1) & d.cap_mask;
+                                    if (lk[j] != 0 || lv[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
                                 }
                             }
                         }
@@ -878,20 +925,28 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
                             qtail += __popc(sb);
                             __syncwarp();
                             if (qtail - qhead >= 32u) { // drain 32 items with every lane busy
+                                PH_MARK(4); // pass 2: wait for probes, classify, enqueue
                                 drain_item<KEYW>(d, wq + (size_t)((qhead + lane) & (Q::CAP - 1)) * Q::IW, cn);
                                 qhead += 32u;
                                 __syncwarp();
+                                PH_MARK(5); // drain (slow path)
                             }
                         }
                     }
                 }
             }
+            PH_MARK(4);
             __syncwarp(); // the group's LUTs are rewritten by the next parent
         }
         __syncthreads(); // tile arrays are rewritten by the next stage 0
     }
     // ---------------- drain what is left in the warp's queue
     if (lane < (int)(qtail - qhead)) drain_item<KEYW>(d, wq + (size_t)((qhead + lane) & (Q::CAP - 1)) * Q::IW, cn);
+    PH_MARK(5);
+#ifdef PG_PHASE_TIMING
+    if (lane == 0)
+        for (int k = 0; k < 8; k++) atomicAdd(&c->phase[k], (unsigned long long)ph[k]);
+#endif
 
     // ---- close the CTA's open outbox chunks
     if (d.n_parts > 1) {
@@ -924,28 +979,74 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
 }
 
 // Records received from other partitions: dedupe + push (PAStar.cpp:240-250 consume_queue -> enqueue).
+// Same probe discipline as the expand kernel: each thread issues the table loads of 4 records before it looks at
+// any of them; most records are rejected right there (same key, g not better).
 template <int KEYW>
-__global__ void insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs, long long n)
+__global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs, long long n)
 {
     constexpr int XW = KEYW == 1 ? 3 : 4;
+    constexpr int ES = KEYW == 1 ? 2 : 4;
+    constexpr int PF = 4;
     SearchCtrl *c = d.ctrl;
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     int min_b = INT_MAX;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long *r = recs + i * XW;
-        Key<KEYW> key;
-        key.lo = r[0];
-        if constexpr (KEYW == 2) key.hi = r[1];
-        const unsigned long long gf = r[KEYW], pm = r[KEYW + 1];
-        const int gnew = (int)(unsigned)(gf >> 32), f = (int)(unsigned)gf, mask = (int)(unsigned)pm;
-        if (mask == 0) continue; // hole left by the sender's chunked outbox reservation
-        bool is_goal = key.lo == d.goal_lo;
-        if constexpr (KEYW == 2) is_goal = is_goal && key.hi == d.goal_hi;
-        if (is_goal) atomicMin(&c->best_goal, gnew);
-        if (f >= min(c->prune_limit, c->best_goal) && !is_goal) continue;
-        const unsigned before = cn.pushed;
-        upsert_from<KEYW>(d, key, key.hash() & d.cap_mask, gnew, f, mask, cn);
-        if (cn.pushed != before) min_b = min(min_b, f - c->f0);
+    const int limit = min(c->prune_limit, c->best_goal);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n; i0 += stride * PF) {
+        Key<KEYW> key[PF];
+        unsigned long long gf[PF], lk[PF], lv[PF], lw[KEYW == 2 ? PF : 1];
+        unsigned mk[PF];
+        bool live[PF];
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            const long long i = i0 + j * stride;
+            live[j] = i < n;
+            key[j] = Key<KEYW>::zero();
+            gf[j] = 0;
+            mk[j] = 0;
+            lk[j] = lv[j] = 0;
+            if (live[j]) {
+                const unsigned long long *r = recs + i * XW;
+                key[j].lo = r[0];
+                if constexpr (KEYW == 2) key[j].hi = r[1];
+                gf[j] = r[KEYW];
+                mk[j] = (unsigned)r[KEYW + 1];
+                if (mk[j] == 0) live[j] = false; // hole left by the sender's chunked outbox reservation
+            }
+            if (live[j]) {
+                bool is_goal = key[j].lo == d.goal_lo;
+                if constexpr (KEYW == 2) is_goal = is_goal && key[j].hi == d.goal_hi;
+                if (is_goal) atomicMin(&c->best_goal, (int)(unsigned)(gf[j] >> 32));
+                if ((int)(unsigned)gf[j] >= limit && !is_goal) live[j] = false;
+            }
+            if (live[j]) {
+                const unsigned long long *e = d.table + home_slot<KEYW>(key[j], d.kb, d.cap_mask) * ES;
+                ld_cg_v2(e, lk[j], lv[j]);
+                if constexpr (KEYW == 2) lw[j] = ld_cg_u64(e + 2);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            if (!live[j]) continue;
+            const int gnew = (int)(unsigned)(gf[j] >> 32), f = (int)(unsigned)gf[j];
+            unsigned long long start = home_slot<KEYW>(key[j], d.kb, d.cap_mask);
+            if constexpr (KEYW == 1) {
+                if (lk[j] == key[j].lo + 1) {
+                    if ((unsigned)gnew >= (unsigned)((~lv[j]) >> 32)) continue; // not better: drop
+                } else if (lk[j] != 0) {
+                    start = next_slot<KEYW>(start, d.cap_mask);
+                }
+            } else {
+                if (lk[j] == key[j].lo && lv[j] == (key[j].hi | (1ull << 63))) {
+                    if ((unsigned)gnew >= (unsigned)((~lw[j]) >> 32)) continue;
+                } else if (lk[j] != 0 || lv[j] != 0) {
+                    start = next_slot<KEYW>(start, d.cap_mask);
+                }
+            }
+            const unsigned before = cn.pushed;
+            upsert_from<KEYW>(d, key[j], start, gnew, f, (int)mk[j], cn);
+            if (cn.pushed != before) min_b = min(min_b, f - c->f0);
+        }
     }
     // A node from another partition may have a lower f than anything open here (or this partition's open list may
     // have run empty): pull the select cursor back so the next round sees it.
@@ -1024,10 +1125,10 @@ __global__ void backtrace_kernel(const __grid_constant__ DevProblem p, const __g
         if (origin || cols >= max_cols) break;
         // read-only probe
         constexpr int ES = KEYW == 1 ? 2 : 4;
-        unsigned long long slot = key.hash() & d.cap_mask;
+        unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
         unsigned long long val = 0;
         bool found = false;
-        for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+        for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
             const unsigned long long *e = d.table + slot * ES;
             if constexpr (KEYW == 1) {
                 if (e[0] == key.lo + 1) {
@@ -1069,9 +1170,9 @@ __global__ void lookup_kernel(const __grid_constant__ DevProblem p, const __grid
     Key<KEYW> key = Key<KEYW>::zero();
     for (int i = 0; i < p.n; i++) key.add_val((unsigned)pos[i], i * p.key_bits);
     constexpr int ES = KEYW == 1 ? 2 : 4;
-    unsigned long long slot = key.hash() & d.cap_mask;
+    unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
     out[0] = 0;
-    for (int probe = 0; probe < MAX_PROBE; probe++, slot = (slot + 1) & d.cap_mask) {
+    for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
         const unsigned long long *e = d.table + slot * ES;
         bool hit, empty;
         unsigned long long val;
@@ -1144,6 +1245,7 @@ DevSearch dev_search(const pg_ctx *ctx)
     DevSearch d;
     d.table = (unsigned long long *)s->d_table;
     d.cap_mask = s->cap - 1;
+    d.kb = ctx->dp.key_bits;
     d.buckets = s->d_buckets;
     d.tail = s->d_tail;
     d.hint = s->d_hint;
@@ -1294,6 +1396,9 @@ void fill_counters(const SearchState *s, pg_result *r)
     r->kernel_ms = s->kernel_ms;
     r->expand_ms = s->expand_ms;
     r->select_ms = s->select_ms;
+#ifdef PG_PHASE_TIMING
+    fprintf(stderr, "phase warp-cycles: barrier %llu claim %llu prepare %llu pass1 %llu pass2 %llu drain %llu\n", c->phase[0], c->phase[1], c->phase[2], c->phase[3], c->phase[4], c->phase[5]);
+#endif
 }
 
 } // namespace
