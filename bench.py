@@ -165,7 +165,7 @@ def run_ours(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches_per_step = 2  # select + fused expand
+    launches_per_step = 4  # select + claim + expand/probe + insert
     extra = {}
     if world == 1:
         G.search_begin(1, 0, cap, batch)
@@ -194,6 +194,7 @@ def run_ours(args, rank, world):
         G.search_profile(False)
         d = {k: c1[k] - c0[k] for k in ("expansions", "generated", "probed", "pushed", "pops")}
         expand_ms, select_ms = c1["expand_ms"] - c0["expand_ms"], c1["select_ms"] - c0["select_ms"]
+        claim_ms, insert_ms = c1["claim_ms"] - c0["claim_ms"], c1["insert_ms"] - c0["insert_ms"]
         total_exp = d["expansions"]
         max_ms = ms
         G.search_end()
@@ -255,19 +256,35 @@ def run_ours(args, rank, world):
     if world == 1:
         hbm, how = measured_peaks()
         P, S, n = G.npairs, G.S, G.n
-        # algorithmic bytes of the fused kernel: per expansion the open-list slot (4) + table entry (16)
-        # + residues (N) + 4 cells per pair (16 P); per probed successor one 32 B table sector; per pushed successor
-        # the sector written back (32) + its open-list slot (4).
-        alg = d["expansions"] * (20 + n + 16 * P) + d["probed"] * 32 + d["pushed"] * 36
-        achieved = alg / (expand_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "search_expand_kernel<7,1>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+        # algorithmic bytes per kernel of the round.  claim: per pop the open-list slot (4) + the table
+        # entry (16), per live parent its compacted record (16).  expand+probe: per expansion the parent record (16) +
+        # residues (N) + 4 cells per pair (16 P), per probed successor one 32 B table sector, per survivor its record
+        # (24).  insert: per survivor the record (24) + its table sector (32); per pushed node the sector written back
+        # (32) + its open-list slot (4).
+        surv = c1.get("survivors", 0) - c0.get("survivors", 0) if "survivors" in c1 else None
+        n_surv = surv if surv else d["pushed"]  # lower bound when the library does not count survivors
+        kern = {
+            "select_kernel": (select_ms, 0.0),
+            "claim_kernel": (claim_ms, d["pops"] * 20.0 + d["expansions"] * 16.0),
+            "expand_probe_kernel<7,1,false>": (expand_ms, d["expansions"] * (16.0 + n + 16 * P) + d["probed"] * 32.0 + n_surv * 24.0),
+            "insert_kernel<1>": (insert_ms, n_surv * 56.0 + d["pushed"] * 36.0),
+        }
+        allk = {}
+        for name, (kms, alg) in kern.items():
+            allk[name] = {"ms_per_step": kms / K, "share_of_step": kms / ms, "algorithmic_bytes_per_launch": alg / K,
+                          "achieved_gbs": (alg / (kms * 1e-3) / 1e9) if kms > 0 else None}
+        top = max((k for k in kern if k != "select_kernel"), key=lambda k: kern[k][0])
+        tms, alg = kern[top]
+        achieved = alg / (tms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                             "frac": achieved / hbm, "traffic": None, "peak_source": how, "launches": K,
-                            "avg_launch_us": 1e3 * expand_ms / K, "algorithmic_bytes_per_launch": alg / K,
-                            "share_of_step": expand_ms / ms, "select_kernel_share": select_ms / ms}
+                            "avg_launch_us": 1e3 * tms / K, "algorithmic_bytes_per_launch": alg / K,
+                            "share_of_step": tms / ms, "kernels": allk,
+                            "whole_round_frac": sum(v[1] for v in kern.values()) / (ms * 1e-3) / 1e9 / hbm}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
-                line["roofline"]["traffic"] = json.load(open(tr)).get("search_expand_dram_bytes_per_launch")
+                line["roofline"]["traffic"] = json.load(open(tr)).get(top)
             except Exception:
                 pass
         # ---- pairwise DP and stand-alone expansion kernel (the other two headline kernels)

@@ -146,6 +146,9 @@ typedef struct {
     double kernel_ms;       /* CUDA-event time from the first to the last round of the search     */
     double expand_ms;       /* sum of the fused expand kernel's launch durations (profiling on)  */
     double select_ms;       /* sum of the select kernel's launch durations (profiling on)        */
+    double claim_ms;        /* ... of the claim kernel (closed-bit claim + compaction of live parents) */
+    double insert_ms;       /* ... of the insert kernel over the round's local survivors          */
+    int64_t survivors;      /* records run through the insert kernel (local survivors + received records) */
 } pg_result;
 
 /* Replaces PAStar<N>::pa_star (pastar/PAStar.cpp:626-673) on ONE GPU
@@ -176,6 +179,17 @@ int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count);
  * bytes per region) while it computes; only the per-destination counts still travel by collective.  Request it
  * with pg_search_config.reserved = 1 in pg_search_begin (no local outbox is allocated). */
 int pg_search_set_peers(pg_ctx *ctx, void *const *peer_inbox, int n);
+/* Device-driven P2P rounds (no host round trip, no collective for the counts): peer_counts[r] is partition r's
+ * uint64[nbuf][n_parts] array as seen from this device.  After its expand kernel a partition stores "records I
+ * wrote into your inbox" at peer_counts[dst][buf][part]; the driver then runs one cross-GPU barrier on the stream
+ * and calls pg_search_insert_inbox_async, whose insert kernels read the counts from device memory.  With nbuf = 2
+ * the inboxes (2 x n_parts regions) and count arrays alternate per round, so that one barrier per round is enough. */
+int pg_search_set_peer_counts(pg_ctx *ctx, void *const *peer_counts, int n, int nbuf);
+/* pg_search_round without the host synchronisation (launches only); pair with pg_search_sync. */
+int pg_search_round_async(pg_ctx *ctx, int32_t f_limit);
+int pg_search_insert_inbox_async(pg_ctx *ctx);
+/* wait for the launched rounds; reports capacity errors like pg_search_round */
+int pg_search_sync(pg_ctx *ctx);
 int64_t pg_search_outbox_capacity(const pg_ctx *ctx);
 /* device pointer to the per-destination record counts of the last round (uint64[64]) */
 int pg_search_outbox_counts_dev(pg_ctx *ctx, void **d_counts);

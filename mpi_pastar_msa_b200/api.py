@@ -38,14 +38,16 @@ class Result(C.Structure):
                 ("expansions", C.c_int64), ("generated", C.c_int64), ("reopen", C.c_int64), ("open_size", C.c_int64),
                 ("closed_size", C.c_int64), ("rounds", C.c_int64), ("probed", C.c_int64), ("pushed", C.c_int64),
                 ("inserted", C.c_int64), ("seconds", C.c_double), ("kernel_ms", C.c_double), ("expand_ms", C.c_double),
-                ("select_ms", C.c_double)]
+                ("select_ms", C.c_double), ("claim_ms", C.c_double), ("insert_ms", C.c_double),
+                ("survivors", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libpastar_gpu.so")
+    # PASTAR_GPU_LIB selects another build of the same library (e.g. one compiled with -DPG_PHASE_TIMING)
+    return os.environ.get("PASTAR_GPU_LIB") or os.path.join(_HERE, "lib", "libpastar_gpu.so")
 
 
 _lib = None
@@ -86,6 +88,10 @@ def load_library():
         "pg_search_insert_dev": ([vp, vp, i64], i32),
         "pg_bench_random_gather": ([i32, i64, C.POINTER(C.c_double)], i32),
         "pg_search_set_peers": ([vp, C.POINTER(vp), i32], i32),
+        "pg_search_set_peer_counts": ([vp, C.POINTER(vp), i32, i32], i32),
+        "pg_search_round_async": ([vp, C.c_int32], i32),
+        "pg_search_insert_inbox_async": ([vp], i32),
+        "pg_search_sync": ([vp], i32),
         "pg_search_outbox_capacity": ([vp], i64),
         "pg_search_outbox_counts_dev": ([vp, C.POINTER(vp)], i32),
         "pg_search_insert_segments_dev": ([vp, vp, i64, C.POINTER(i64), i32], i32),
@@ -102,7 +108,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -306,6 +312,19 @@ class PastarGPU:
     def search_set_peers(self, ptrs):
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         self._ck(self.L.pg_search_set_peers(self.h, arr, len(ptrs)))
+
+    def search_set_peer_counts(self, ptrs, nbuf=2):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._ck(self.L.pg_search_set_peer_counts(self.h, arr, len(ptrs), nbuf))
+
+    def search_round_async(self, f_limit=2**31 - 1):
+        self._ck(self.L.pg_search_round_async(self.h, f_limit))
+
+    def search_insert_inbox_async(self):
+        self._ck(self.L.pg_search_insert_inbox_async(self.h))
+
+    def search_sync(self):
+        self._ck(self.L.pg_search_sync(self.h))
 
     def search_outbox_capacity(self):
         return int(self.L.pg_search_outbox_capacity(self.h))

@@ -72,6 +72,11 @@ struct SearchState {
     SearchCtrl *d_ctrl = nullptr;
     SearchCtrl *h_ctrl = nullptr; // pinned
     uint32_t *d_trace = nullptr;  // backtrace output
+    unsigned long long *d_live = nullptr;  // live parents of the round: (keyw + 1) u64 each
+    unsigned long long *d_surv = nullptr;  // local survivors of the round: pg_xrec records
+    uint64_t surv_cap = 0;
+    unsigned long long *d_host_counts = nullptr; // record counts the host passes to insert launches
+    unsigned long long h_host_counts[64] = {0};
     pg_search_config cfg;
     int64_t batch_target = 0;
     int f0 = 0, f_range = 0, ub = 0;
@@ -81,6 +86,8 @@ struct SearchState {
     unsigned long long *h_outbox_count = nullptr;
     uint64_t outbox_cap = 0; // records per destination
     void *peer_inbox[16] = {nullptr};
+    unsigned long long *peer_counts[16] = {nullptr}; // P2P mode: every partition's uint64[nbuf][n_parts] "records from source s"
+    int p2p_nbuf = 1, p2p_buf = 0;                   // double-buffered inboxes: one cross-GPU barrier per round is enough
     bool p2p = false;
     int xrec = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -88,7 +95,7 @@ struct SearchState {
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
-    double expand_ms = 0, select_ms = 0;
+    double expand_ms = 0, select_ms = 0, claim_ms = 0, insert_ms = 0;
     double kernel_ms = 0;
     int64_t rounds = 0;
     bool active = false;
@@ -221,7 +228,11 @@ struct DevSearch {
     unsigned long long outbox_cap;
     // P2P mode: base of every partition's (peer-mapped) inbox; this partition writes region [part] of inbox[dst]
     char *peer_inbox[16];
+    unsigned long long *peer_counts[16];
     int p2p;
+    unsigned long long *live;     // compacted live parents of the round
+    unsigned long long *surv;     // local survivors of the round
+    unsigned long long surv_cap;
 };
 
 struct Counters { // per thread, flushed once per kernel
@@ -357,7 +368,12 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, lon
     if (t == 0) {
         c->batch_n = 0;
         c->plan_n = 0;
+        if (target > 0) { // a status-only select (target 0) leaves the round's lists alone
+            c->live_n = 0;
+            c->surv_n = 0;
+        }
     }
+    if (target > 0 && d.n_parts > 1 && t < d.n_parts) d.outbox_count[t] = 0;
     if (c->done || c->error) return;
     const int range = c->f_range;
     const int limit_f = min(f_limit, c->best_goal);
@@ -472,38 +488,6 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, lon
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// fused expand + owner + dedupe + push
-// ---------------------------------------------------------------------------------------------
-// Structure of one CTA (256 threads), per tile of 256 popped open-list entries:
-//   stage 0  one thread per entry: plan lookup, table entry load, closed-bit claim (PAStar.cpp:344-351); entries
-//            that are stale (a better g was pushed later) or already closed drop out here, live ones are compacted
-//            into shared memory, so the expansion below only sees nodes that are really expanded.
-//   stage 1  a group of 2^A lanes per live parent: LUT / HH staging (pg_expand_prepare), then per lane
-//            pass 1: compute f, g, key, hash slot of its next successors and ISSUE all their table loads (up to 8
-//                    independent 16 B loads in flight per lane: the probe is latency-bound, not bandwidth-bound);
-//            pass 2: compare.  The common case (same key, g not better: PAStar.cpp:228 / PriorityList.h:109)
-//                    ends here with no atomic and no store.  The rest - new key, better g, hash collision -
-//                    is appended to a per-warp shared-memory queue and
-//            drain:  executed 32 items at a time with all lanes active (CAS on key / value, push to the f bucket),
-//                    so the rare slow path does not serialise the warp.
-#ifdef PG_PHASE_TIMING
-#define PH_MARK(idx) do { long long t__ = clock64(); ph[idx] += t__ - ph_t; ph_t = t__; } while (0)
-#else
-#define PH_MARK(idx) do { } while (0)
-#endif
-
-struct OwnerArgs {
-    int type, shift, nb;
-    int sh[8];
-};
-
-template <int KEYW>
-struct SlowQ {
-    static constexpr int IW = KEYW == 1 ? 4 : 6; // u64 words per item
-    static constexpr int CAP = 64;               // items per warp (ring)
-};
-
 // slow path for one successor: find/claim its slot starting at `slot`, install g if strictly better, push.
 template <int KEYW>
 __device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> &key, unsigned long long slot, int gnew, int f, int mask,
@@ -578,14 +562,93 @@ __device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> 
     bucket_push(d, f, (uint32_t)slot);
 }
 
+// ---------------------------------------------------------------------------------------------
+// the search round: select -> claim -> expand + probe -> insert
+// ---------------------------------------------------------------------------------------------
+// claim   one thread per popped open-list entry: plan lookup, closed-bit claim (PAStar.cpp:344-351).  Entries
+//         that are stale (a better g was pushed later) or already closed drop out here; the live parents are
+//         compacted into d.live, so the expansion only sees nodes that are really expanded and needs no barrier.
+// expand  a group of 2^A lanes per live parent, no CTA-wide synchronisation in the loop: LUT / HH staging
+//         (pg_expand_prepare), then per lane
+//            pass 1: f, g, key, owner and home slot of its next successors; ISSUE all their table loads (up to 8
+//                    independent 16 B loads in flight per lane);
+//            pass 2: compare.  The common case (same key, g not better: PAStar.cpp:228 / PriorityList.h:109)
+//                    ends here: the kernel only READS the table.  Survivors - new key, better g, hash collision -
+//                    are staged in a per-warp shared-memory ring and appended 32 at a time, coalesced, to the
+//                    round's survivor list.  Successors owned by another partition go to that partition's outbox
+//                    (or straight into its peer-mapped inbox over NVLink) unprobed: the owner filters them.
+// insert  survivors and records received from other partitions: CAS on key / value, push to the f bucket
+//         (PAStar.cpp:219-237 enqueue, PriorityList.h:104-113 conditional_enqueue), 4 records in flight per thread.
+#ifdef PG_PHASE_TIMING
+#define PH_MARK(idx) do { long long t__ = clock64(); ph[idx] += t__ - ph_t; ph_t = t__; } while (0)
+#else
+#define PH_MARK(idx) do { } while (0)
+#endif
+
+struct OwnerArgs {
+    int type, shift, nb;
+    int sh[8];
+};
+
+constexpr unsigned long long HINT_FLAG = 1ull << 31; // record word KEYW+1: {start slot : 32 | HINT_FLAG | move mask : 16}
+constexpr int RING_CAP = 64;                         // survivor ring, items per warp
+constexpr int PLAN_SM = 2048;
+
 template <int KEYW>
-__device__ __forceinline__ void drain_item(const DevSearch &d, const unsigned long long *it, Counters &cn)
+__global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevSearch d)
 {
-    Key<KEYW> key;
-    key.lo = it[0];
-    if constexpr (KEYW == 2) key.hi = it[1];
-    const unsigned long long slot = it[KEYW], gf = it[KEYW + 1], m = it[KEYW + 2];
-    upsert_from<KEYW>(d, key, slot, (int)(unsigned)(gf >> 32), (int)(unsigned)gf, (int)(unsigned)m, cn);
+    __shared__ uint32_t s_plan[PLAN_SM];
+    SearchCtrl *c = d.ctrl;
+    const int batch_n = (c->done || c->error) ? 0 : c->batch_n;
+    if (batch_n == 0) return;
+    const int plan_n = c->plan_n;
+    const bool plan_sm = plan_n <= PLAN_SM;
+    if (plan_sm)
+        for (int i = threadIdx.x; i < plan_n; i += blockDim.x) s_plan[i] = d.plan[i].offset;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = blockIdx.x * 256; base < batch_n; base += gridDim.x * 256) {
+        const int bi = base + threadIdx.x;
+        bool live = false;
+        unsigned long long klo = 0, khi = 0, val = 0;
+        if (bi < batch_n) {
+            int lo = 0, hi = plan_n - 1;
+            while (lo < hi) { // last plan entry with offset <= bi
+                const int mid = (lo + hi + 1) >> 1;
+                const uint32_t off = plan_sm ? s_plan[mid] : d.plan[mid].offset;
+                if ((int)off <= bi)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const PlanEntry pe = d.plan[lo];
+            const uint32_t slot = d.pool[(size_t)pe.unit * UNIT + pe.start + (bi - pe.offset)];
+            unsigned long long *e = d.table + (size_t)slot * (KEYW == 1 ? 2 : 4);
+            // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion
+            const unsigned long long old = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
+            if (!(old & OPEN_BIT)) {
+                live = true;
+                val = ~old;
+                if constexpr (KEYW == 1) {
+                    klo = ld_cg_u64(e) - 1;
+                } else {
+                    klo = ld_cg_u64(e);
+                    khi = ld_cg_u64(e + 1) & ~(1ull << 63);
+                }
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&c->live_n, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (live) {
+            unsigned long long *r = d.live + (size_t)(wbase + __popc(bal & lt)) * (KEYW + 1);
+            r[0] = klo;
+            if constexpr (KEYW == 2) r[1] = khi;
+            r[KEYW] = val;
+        }
+    }
 }
 
 // Outbox space is handed out in chunks of OBOX_CHUNK records per (CTA, destination): one global atomic per chunk,
@@ -609,7 +672,7 @@ __device__ __forceinline__ void outbox_mark_holes(const DevSearch &d, int dst, u
     for (unsigned i = from; i < OBOX_CHUNK; i++) r[(size_t)i * XW + KEYW + 1] = 0ull;
 }
 template <int KEYW>
-__device__ __forceinline__ unsigned long long outbox_reserve(const DevSearch &d, unsigned long long *s_obox, int dst, int k)
+__device__ __noinline__ unsigned long long outbox_reserve(const DevSearch &d, unsigned long long *s_obox, int dst, int k)
 {
     for (;;) {
         const unsigned long long st = atomicAdd(&s_obox[dst], (unsigned long long)k);
@@ -631,42 +694,46 @@ __device__ __forceinline__ unsigned long long outbox_reserve(const DevSearch &d,
     }
 }
 
-template <int N, int KEYW>
-__global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
-                                                               const __grid_constant__ OwnerArgs oa)
+// Append `count` (<= 32) ring items, contiguous from ring index `from`, to the round's survivor list: one atomic,
+// coalesced 8-byte stores.
+template <int XW>
+__device__ __forceinline__ void ring_flush(const DevSearch &d, const unsigned long long *wq, unsigned from, unsigned count, int lane)
+{
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&d.ctrl->surv_n, (unsigned long long)count);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + count > d.surv_cap) {
+        d.ctrl->error = 4;
+        return;
+    }
+    const unsigned long long *src = wq + (size_t)(from & (RING_CAP - 1)) * XW;
+    unsigned long long *dst = d.surv + base * XW;
+    for (unsigned w = lane; w < count * XW; w += 32) dst[w] = src[w];
+}
+
+template <int N, int KEYW, bool MULTI>
+__global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
+                                                              const __grid_constant__ OwnerArgs oa)
 {
     using C = ExpCfg<N>;
-    using Q = SlowQ<KEYW>;
+    constexpr int XW = KEYW == 1 ? 3 : 4;
     constexpr int GROUPS = 256 / C::LP;
+    constexpr int GPW = 32 / C::LP; // parent groups per warp
     constexpr int NI = 1 << C::IB;
     constexpr int PFMAX = KEYW == 1 ? 8 : 4;
     constexpr int PF = NI < PFMAX ? NI : PFMAX; // successors whose table loads are in flight together, per lane
-    constexpr int PLAN_SM = 1024;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairMeta *meta = reinterpret_cast<PairMeta *>(smem_raw);
     Key<KEYW> *s_keyhigh = reinterpret_cast<Key<KEYW> *>(smem_raw + ((sizeof(PairMeta) + 15) & ~size_t(15)));
-    unsigned long long *s_tkey = reinterpret_cast<unsigned long long *>(s_keyhigh + C::H); // [KEYW][256]
-    unsigned long long *s_tval = s_tkey + KEYW * 256;
-    unsigned long long *s_queue = s_tval + 256; // [8 warps][CAP][IW]
-    uint32_t *s_plan = reinterpret_cast<uint32_t *>(s_queue + 8 * Q::CAP * Q::IW);
-    int *s_groups = reinterpret_cast<int *>(s_plan + PLAN_SM);
-    __shared__ unsigned long long s_cnt[8];
-    __shared__ int s_ctl[4];
-    __shared__ int s_tcount;
-    __shared__ unsigned long long s_obox[64];
+    unsigned long long *s_ring = reinterpret_cast<unsigned long long *>(s_keyhigh + C::H); // [8 warps][RING_CAP][XW]
+    int *s_groups = reinterpret_cast<int *>(s_ring + 8 * RING_CAP * XW);
+    __shared__ unsigned long long s_cnt[4];
+    __shared__ unsigned long long s_obox[MULTI ? 64 : 1];
 
     SearchCtrl *c = d.ctrl;
-    if (threadIdx.x == 0) { // one reader, so the whole CTA takes the same early exit
-        s_ctl[0] = (c->done || c->error) ? 0 : c->batch_n;
-        s_ctl[1] = c->plan_n;
-        s_ctl[2] = min(c->prune_limit, c->best_goal);
-    }
-    __syncthreads();
-    const int batch_n = s_ctl[0];
-    if (batch_n == 0) return;
-    const int plan_n = s_ctl[1];
-    const int limit = s_ctl[2];
-    const bool plan_sm = plan_n <= PLAN_SM;
+    const int live_n = (c->done || c->error) ? 0 : c->live_n;
+    if (live_n == 0) return;
+    const int limit = min(c->prune_limit, c->best_goal);
 
     pg_load_pair_meta(p, meta);
     for (int hi = threadIdx.x; hi < C::H; hi += blockDim.x) {
@@ -675,10 +742,8 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
             if ((hi >> b) & 1) k.add_bit((C::A + b) * p.key_bits);
         s_keyhigh[hi] = k;
     }
-    if (plan_sm)
-        for (int i = threadIdx.x; i < plan_n; i += blockDim.x) s_plan[i] = d.plan[i].offset;
-    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x < 64) s_obox[threadIdx.x] = (unsigned long long)OBOX_CHUNK; // no chunk yet: the first append opens one
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (MULTI && threadIdx.x < 64) s_obox[threadIdx.x] = (unsigned long long)OBOX_CHUNK; // no chunk yet: the first append opens one
     __syncthreads();
 
     const int grp = threadIdx.x / C::LP, sub = threadIdx.x % C::LP;
@@ -688,260 +753,208 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     int *s_grp = s_groups + grp * C::GROUP_INTS;
     const int *s_hhg = s_grp + 8 * C::P;
     const int *s_hhh = s_hhg + C::H;
-    unsigned long long *wq = s_queue + (size_t)warp * Q::CAP * Q::IW;
-    unsigned qhead = 0, qtail = 0; // warp-uniform ring indices
+    unsigned long long *wq = s_ring + (size_t)warp * RING_CAP * XW;
+    unsigned qhead = 0, qtail = 0; // warp-uniform ring indices; qhead is always a multiple of 32
 #ifdef PG_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long ph_t = clock64();
 #endif
-    Counters cn = {0, 0, 0, 0, 0, 0, 0};
+    unsigned n_exp = 0, n_gen = 0, n_pruned = 0;
     const unsigned fmask = (1u << p.key_bits) - 1u;
     const int full = (1 << N) - 1;
 
-    for (int tbase = blockIdx.x * 256; tbase < batch_n; tbase += gridDim.x * 256) {
-        if (threadIdx.x == 0) s_tcount = 0;
-        __syncthreads();
-        PH_MARK(0); // barrier / tile turnover
-        // ---------------- stage 0: claim
-        {
-            const int bi = tbase + threadIdx.x;
-            bool live = false;
-            unsigned long long klo = 0, khi = 0, val = 0;
-            if (bi < batch_n) {
-                int lo = 0, hi = plan_n - 1;
-                while (lo < hi) { // last plan entry with offset <= bi
-                    const int mid = (lo + hi + 1) >> 1;
-                    const uint32_t off = plan_sm ? s_plan[mid] : d.plan[mid].offset;
-                    if ((int)off <= bi)
-                        lo = mid;
-                    else
-                        hi = mid - 1;
-                }
-                const PlanEntry pe = d.plan[lo];
-                const uint32_t slot = d.pool[(size_t)pe.unit * UNIT + pe.start + (bi - pe.offset)];
-                unsigned long long *e = d.table + (size_t)slot * (KEYW == 1 ? 2 : 4);
-                // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion
-                const unsigned long long old = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
-                if (!(old & OPEN_BIT)) {
-                    live = true;
-                    val = ~old;
-                    if constexpr (KEYW == 1) {
-                        klo = ld_cg_u64(e) - 1;
-                    } else {
-                        klo = ld_cg_u64(e);
-                        khi = ld_cg_u64(e + 1) & ~(1ull << 63);
-                    }
-                } else {
-                    cn.stale++;
-                }
+    // parents are dealt to the groups round-robin; the trip count is warp-uniform (the ring is a warp-level structure)
+    const int stride = gridDim.x * GROUPS;
+    int pi = blockIdx.x * GROUPS + grp;
+    unsigned long long nk0 = 0, nk1 = 0, nval = 0;
+    if (pi < live_n) {
+        const unsigned long long *r = d.live + (size_t)pi * (KEYW + 1);
+        nk0 = __ldg(r);
+        if constexpr (KEYW == 2) nk1 = __ldg(r + 1);
+        nval = __ldg(r + KEYW);
+    }
+    for (int wfirst = blockIdx.x * GROUPS + warp * GPW; wfirst < live_n; wfirst += stride, pi += stride) {
+        bool act = pi < live_n;
+        Key<KEYW> pkey = Key<KEYW>::zero();
+        pkey.lo = nk0;
+        if constexpr (KEYW == 2) pkey.hi = nk1;
+        const unsigned long long val = nval;
+        if (pi + stride < live_n) { // the next parent's record travels while this one is expanded
+            const unsigned long long *r = d.live + (size_t)(pi + stride) * (KEYW + 1);
+            nk0 = __ldg(r);
+            if constexpr (KEYW == 2) nk1 = __ldg(r + 1);
+            nval = __ldg(r + KEYW);
+        }
+        int pos[N];
+        int goal_mask = 0;
+        ExpLane<N> L;
+        L.alive = 0;
+        if (act) {
+            const int g = (int)(unsigned)(val >> 32), parenti = (int)(val & 0xffffu);
+            int alive = 0, onestep = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                pos[i] = (int)pkey.field(i * p.key_bits, fmask);
+                alive |= (pos[i] < p.len[i]) << i;
+                onestep |= (pos[i] + 1 == p.len[i]) << i;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, live);
-            int wbase = 0;
-            if (lane == 0 && bal) wbase = atomicAdd(&s_tcount, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (live) {
-                const int idx = wbase + __popc(bal & lt);
-                s_tkey[idx] = klo;
-                if constexpr (KEYW == 2) s_tkey[256 + idx] = khi;
-                s_tval[idx] = val;
+            if (alive == 0) {
+                act = false; // the goal itself: never expanded (PAStar.cpp:353-357)
+            } else {
+                // the goal is reached from here by moving every sequence that is one short of its end
+                goal_mask = alive == onestep ? alive : 0;
+                if (sub == 0) n_exp++;
+                pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
             }
         }
-        PH_MARK(1); // stage 0 claim
-        __syncthreads();
-        PH_MARK(0);
-        const int nlive = s_tcount;
-        const int iters = (nlive + GROUPS - 1) / GROUPS;
+        PH_MARK(2); // prepare (LUT gathers, HH, B/E)
+        Key<KEYW> klow = pkey;
+#pragma unroll
+        for (int i = 0; i < C::A; i++)
+            if ((sub >> i) & 1) klow.add_bit(i * p.key_bits);
+        const bool interior = L.alive == full;
 
-        // ---------------- stage 1: expand the live parents
-        for (int it = 0; it < iters; it++) {
-            const int pi = it * GROUPS + grp;
-            bool act = pi < nlive;
-            Key<KEYW> pkey = Key<KEYW>::zero();
-            int pos[N];
-            int g = 0, parenti = 0, goal_mask = 0;
-            ExpLane<N> L;
-            L.alive = 0;
-            if (act) {
-                pkey.lo = s_tkey[pi];
-                if constexpr (KEYW == 2) pkey.hi = s_tkey[256 + pi];
-                const unsigned long long val = s_tval[pi];
-                g = (int)(unsigned)(val >> 32);
-                parenti = (int)(val & 0xffffu);
-                int alive = 0, onestep = 0;
+        for (int u = 0; u < (1 << C::UB); u++) {
+            int vg[NI], vh[NI];
+            pg_expand_block<N>(L, u, vg, vh);
 #pragma unroll
-                for (int i = 0; i < N; i++) {
-                    pos[i] = (int)pkey.field(i * p.key_bits, fmask);
-                    alive |= (pos[i] < p.len[i]) << i;
-                    onestep |= (pos[i] + 1 == p.len[i]) << i;
-                }
-                if (alive == 0) {
-                    act = false; // the goal itself: never expanded (PAStar.cpp:353-357)
-                } else {
-                    // the goal is reached from here by moving every sequence that is one short of its end
-                    goal_mask = alive == onestep ? alive : 0;
-                    if (sub == 0) cn.expansions++;
-                    pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
-                }
-            }
-            PH_MARK(2); // prepare (LUT gathers, HH, B/E)
-            Key<KEYW> klow = pkey;
+            for (int cb = 0; cb < NI; cb += PF) {
+                unsigned long long lk[PF], lv[PF];
+                unsigned long long lw[KEYW == 2 ? PF : 1]; // KEYW=2: the value word
+                uint32_t ls[PF];
+                int lg[PF];
+                unsigned vmask = 0;
+                // ---- pass 1: issue the probes
 #pragma unroll
-            for (int i = 0; i < C::A; i++)
-                if ((sub >> i) & 1) klow.add_bit(i * p.key_bits);
-            const bool interior = L.alive == full;
-
-            for (int u = 0; u < (1 << C::UB); u++) {
-                int vg[NI], vh[NI];
-                pg_expand_block<N>(L, u, vg, vh);
+                for (int j = 0; j < PF; j++) {
+                    const int i = cb + j;
+                    const int high = (u << C::IB) | i;
+                    const int mask = (high << C::A) | sub;
+                    bool v = act && mask != 0 && (interior || !(mask & ~L.alive));
+                    bool rem = false;
+                    int rown = 0;
+                    lk[j] = lv[j] = 0;
+                    ls[j] = 0;
+                    lg[j] = 0;
+                    if (v) {
+                        const int gn = vg[i] + s_hhg[high];
+                        const int f = gn + vh[i] + s_hhh[high];
+                        n_gen++;
+                        const bool is_goal = mask == goal_mask;
+                        if (is_goal) atomicMin(&c->best_goal, gn);
+                        if (f >= limit && !is_goal) {
+                            n_pruned++;
+                            v = false;
+                        }
+                        lg[j] = gn;
+                    }
+                    if (v) {
+                        const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                        if constexpr (MULTI) {
+                            unsigned own;
+                            if (oa.type == PG_HASH_FSUM || oa.type == PG_HASH_PSUM) {
+                                unsigned s = 0;
+                                const int nd = oa.type == PG_HASH_PSUM ? 2 : N;
+                                for (int q = 0; q < nd; q++) s += key.field(q * p.key_bits, fmask);
+                                own = (s >> oa.shift) % (unsigned)d.n_parts;
+                            } else {
+                                unsigned w = 0;
 #pragma unroll
-                for (int cb = 0; cb < NI; cb += PF) {
-                    unsigned long long lk[PF], lv[PF];
-                    unsigned long long lw[KEYW == 2 ? PF : 1]; // KEYW=2: the value word
-                    uint32_t ls[PF];
-                    int lg[PF];
-                    unsigned vmask = 0;
-                    // ---- pass 1: issue the probes
-#pragma unroll
-                    for (int j = 0; j < PF; j++) {
-                        const int i = cb + j;
-                        const int high = (u << C::IB) | i;
-                        const int mask = (high << C::A) | sub;
-                        bool v = act && mask != 0 && (interior || !(mask & ~L.alive));
-                        bool rem = false;
-                        int rown = 0;
-                        Key<KEYW> rkey = Key<KEYW>::zero();
-                        lk[j] = lv[j] = 0;
-                        ls[j] = 0;
-                        lg[j] = 0;
-                        if (v) {
-                            const int gn = vg[i] + s_hhg[high];
-                            const int f = gn + vh[i] + s_hhh[high];
-                            cn.generated++;
-                            const bool is_goal = mask == goal_mask;
-                            if (is_goal) atomicMin(&c->best_goal, gn);
-                            if (f >= limit && !is_goal) {
-                                cn.pruned++;
+                                for (int m = 0; m < 8; m++)
+                                    if (m < oa.nb && oa.sh[m] >= 0) w |= key.field(oa.sh[m], 1u) << m;
+                                own = w % (unsigned)d.n_parts;
+                            }
+                            if ((int)own != d.part) { // remote successor: goes to the owner's outbox below
+                                rem = true;
+                                rown = (int)own;
                                 v = false;
                             }
-                            lg[j] = gn;
                         }
                         if (v) {
-                            const Key<KEYW> key = klow.plus(s_keyhigh[high]);
-                            if (d.n_parts > 1) {
-                                unsigned own;
-                                if (oa.type == PG_HASH_FSUM || oa.type == PG_HASH_PSUM) {
-                                    unsigned s = 0;
-                                    const int nd = oa.type == PG_HASH_PSUM ? 2 : N;
-                                    for (int q = 0; q < nd; q++) s += key.field(q * p.key_bits, fmask);
-                                    own = (s >> oa.shift) % (unsigned)d.n_parts;
-                                } else {
-                                    unsigned w = 0;
-#pragma unroll
-                                    for (int m = 0; m < 8; m++)
-                                        if (m < oa.nb && oa.sh[m] >= 0) w |= key.field(oa.sh[m], 1u) << m;
-                                    own = w % (unsigned)d.n_parts;
-                                }
-                                if ((int)own != d.part) { // remote successor: goes to the owner's outbox below
-                                    rem = true;
-                                    rown = (int)own;
-                                    rkey = key;
-                                    v = false;
-                                }
-                            }
-                            if (v) {
-                                const unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
-                                ls[j] = (uint32_t)slot;
-                                const unsigned long long *e = d.table + slot * (KEYW == 1 ? 2 : 4);
-                                if constexpr (KEYW == 1) {
-                                    ld_cg_v2(e, lk[j], lv[j]);
-                                } else {
-                                    ld_cg_v2(e, lk[j], lv[j]); // 32 B entry {k0, k1, val, pad}
-                                    lw[j] = ld_cg_u64(e + 2);
-                                }
-                                vmask |= 1u << j;
-                            }
-                        }
-                        if (d.n_parts > 1) { // warp-uniform: one reservation per (warp, destination) from the CTA's outbox chunks
-                            unsigned todo = __ballot_sync(0xffffffffu, rem);
-                            while (todo) {
-                                const int leader = __ffs(todo) - 1;
-                                const int dst = __shfl_sync(0xffffffffu, rown, leader);
-                                const unsigned same = __ballot_sync(0xffffffffu, rem && rown == dst);
-                                unsigned long long pos0 = 0;
-                                if (lane == leader) pos0 = outbox_reserve<KEYW>(d, s_obox, dst, __popc(same));
-                                pos0 = __shfl_sync(0xffffffffu, pos0, leader);
-                                if (rem && rown == dst) {
-                                    unsigned long long *r = outbox_record<KEYW>(d, dst, pos0 + __popc(same & lt));
-                                    const int f = lg[j] + vh[cb + j] + s_hhh[(u << C::IB) | (cb + j)];
-                                    r[0] = rkey.lo;
-                                    if constexpr (KEYW == 2) r[1] = rkey.hi;
-                                    r[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)f;
-                                    r[KEYW + 1] = (unsigned long long)(unsigned)mask;
-                                }
-                                todo &= ~same;
-                            }
+                            const unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
+                            ls[j] = (uint32_t)slot;
+                            const unsigned long long *e = d.table + slot * (KEYW == 1 ? 2 : 4);
+                            ld_cg_v2(e, lk[j], lv[j]); // KEYW=2: 32 B entry {k0, k1, val, pad}
+                            if constexpr (KEYW == 2) lw[j] = ld_cg_u64(e + 2);
+                            vmask |= 1u << j;
                         }
                     }
-                    PH_MARK(3); // pass 1: issue probes (+ remote appends)
-                    // ---- pass 2: classify; queue what needs an atomic
-#pragma unroll
-                    for (int j = 0; j < PF; j++) {
-                        const int i = cb + j;
-                        const int high = (u << C::IB) | i;
-                        const int mask = (high << C::A) | sub;
-                        bool slow = false;
-                        unsigned long long start = ls[j];
-                        Key<KEYW> key = Key<KEYW>::zero();
-                        if ((vmask >> j) & 1u) {
-                            key = klow.plus(s_keyhigh[high]);
-                            if constexpr (KEYW == 1) {
-                                if (lk[j] == key.lo + 1) {
-                                    const unsigned g_old = (unsigned)((~lv[j]) >> 32);
-                                    slow = (unsigned)lg[j] < g_old; // better g: needs the CAS
-                                } else {
-                                    slow = true; // empty slot or collision
-                                    if (lk[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
-                                }
-                            } else {
-                                if (lk[j] == key.lo && lv[j] == (key.hi | (1ull << 63))) {
-                                    const unsigned g_old = (unsigned)((~lw[j]) >> 32);
-                                    slow = (unsigned)lg[j] < g_old;
-                                } else {
-                                    slow = true;
-                                    if (lk[j] != 0 || lv[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
-                                }
+                    if constexpr (MULTI) { // one reservation per (warp, destination) from the CTA's outbox chunks
+                        unsigned todo = __ballot_sync(0xffffffffu, rem);
+                        while (todo) {
+                            const int leader = __ffs(todo) - 1;
+                            const int dst = __shfl_sync(0xffffffffu, rown, leader);
+                            const unsigned same = __ballot_sync(0xffffffffu, rem && rown == dst);
+                            unsigned long long pos0 = 0;
+                            if (lane == leader) pos0 = outbox_reserve<KEYW>(d, s_obox, dst, __popc(same));
+                            pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+                            if (rem && rown == dst) {
+                                unsigned long long *r = outbox_record<KEYW>(d, dst, pos0 + __popc(same & lt));
+                                const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                                const int f = lg[j] + vh[i] + s_hhh[high];
+                                r[0] = key.lo;
+                                if constexpr (KEYW == 2) r[1] = key.hi;
+                                r[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)f;
+                                r[KEYW + 1] = (unsigned long long)(unsigned)mask;
                             }
-                        }
-                        const unsigned sb = __ballot_sync(0xffffffffu, slow);
-                        if (sb) {
-                            if (slow) {
-                                unsigned long long *q = wq + (size_t)((qtail + __popc(sb & lt)) & (Q::CAP - 1)) * Q::IW;
-                                q[0] = key.lo;
-                                if constexpr (KEYW == 2) q[1] = key.hi;
-                                q[KEYW] = start;
-                                q[KEYW + 1] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)(lg[j] + vh[i] + s_hhh[high]);
-                                q[KEYW + 2] = (unsigned long long)(unsigned)mask;
-                            }
-                            qtail += __popc(sb);
-                            __syncwarp();
-                            if (qtail - qhead >= 32u) { // drain 32 items with every lane busy
-                                PH_MARK(4); // pass 2: wait for probes, classify, enqueue
-                                drain_item<KEYW>(d, wq + (size_t)((qhead + lane) & (Q::CAP - 1)) * Q::IW, cn);
-                                qhead += 32u;
-                                __syncwarp();
-                                PH_MARK(5); // drain (slow path)
-                            }
+                            todo &= ~same;
                         }
                     }
                 }
+                PH_MARK(3); // pass 1: issue probes (+ remote appends)
+                // ---- pass 2: compare; stage the survivors
+#pragma unroll
+                for (int j = 0; j < PF; j++) {
+                    const int i = cb + j;
+                    const int high = (u << C::IB) | i;
+                    const int mask = (high << C::A) | sub;
+                    bool slow = false;
+                    unsigned long long start = ls[j];
+                    Key<KEYW> key = Key<KEYW>::zero();
+                    if ((vmask >> j) & 1u) {
+                        key = klow.plus(s_keyhigh[high]);
+                        if constexpr (KEYW == 1) {
+                            if (lk[j] == key.lo + 1) {
+                                const unsigned g_old = (unsigned)((~lv[j]) >> 32);
+                                slow = (unsigned)lg[j] < g_old; // better g
+                            } else {
+                                slow = true; // empty slot or collision
+                                if (lk[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
+                            }
+                        } else {
+                            if (lk[j] == key.lo && lv[j] == (key.hi | (1ull << 63))) {
+                                const unsigned g_old = (unsigned)((~lw[j]) >> 32);
+                                slow = (unsigned)lg[j] < g_old;
+                            } else {
+                                slow = true;
+                                if (lk[j] != 0 || lv[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
+                            }
+                        }
+                    }
+                    const unsigned sb = __ballot_sync(0xffffffffu, slow);
+                    if (sb) {
+                        if (slow) {
+                            unsigned long long *q = wq + (size_t)((qtail + __popc(sb & lt)) & (RING_CAP - 1)) * XW;
+                            q[0] = key.lo;
+                            if constexpr (KEYW == 2) q[1] = key.hi;
+                            q[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)(lg[j] + vh[i] + s_hhh[high]);
+                            q[KEYW + 1] = (start << 32) | HINT_FLAG | (unsigned long long)(unsigned)mask;
+                        }
+                        qtail += __popc(sb);
+                        __syncwarp();
+                        if (qtail - qhead >= 32u) {
+                            ring_flush<XW>(d, wq, qhead, 32u, lane);
+                            qhead += 32u;
+                            __syncwarp();
+                        }
+                    }
+                }
+                PH_MARK(4); // pass 2: wait for the probes, compare, stage
             }
-            PH_MARK(4);
-            __syncwarp(); // the group's LUTs are rewritten by the next parent
         }
-        __syncthreads(); // tile arrays are rewritten by the next stage 0
+        __syncwarp(); // the group's LUTs are rewritten by the next parent
     }
-    // ---------------- drain what is left in the warp's queue
-    if (lane < (int)(qtail - qhead)) drain_item<KEYW>(d, wq + (size_t)((qhead + lane) & (Q::CAP - 1)) * Q::IW, cn);
+    if (qtail != qhead) ring_flush<XW>(d, wq, qhead, qtail - qhead, lane);
     PH_MARK(5);
 #ifdef PG_PHASE_TIMING
     if (lane == 0)
@@ -949,7 +962,7 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
 #endif
 
     // ---- close the CTA's open outbox chunks
-    if (d.n_parts > 1) {
+    if constexpr (MULTI) {
         __syncthreads();
         if ((int)threadIdx.x < d.n_parts) {
             const unsigned long long st = s_obox[threadIdx.x];
@@ -959,9 +972,9 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     }
     // ---- counters: one atomic per CTA per counter
     {
-        unsigned v[6] = {cn.expansions, cn.generated, cn.reopen, cn.inserted, cn.pushed, cn.pruned};
+        unsigned v[3] = {n_exp, n_gen, n_pruned};
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
+        for (int k = 0; k < 3; k++) {
             unsigned x = v[k];
             for (int o = 16; o; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
             if (lane == 0 && x) atomicAdd(&s_cnt[k], (unsigned long long)x);
@@ -971,30 +984,31 @@ __global__ void __launch_bounds__(256, 3) search_expand_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         atomicAdd(&c->expansions, s_cnt[0]);
         atomicAdd(&c->generated, s_cnt[1]);
-        atomicAdd(&c->reopen, s_cnt[2]);
-        atomicAdd(&c->inserted, s_cnt[3]);
-        atomicAdd(&c->pushed, s_cnt[4]);
-        atomicAdd(&c->pruned, s_cnt[5]);
+        atomicAdd(&c->pruned, s_cnt[2]);
     }
 }
 
-// Records received from other partitions: dedupe + push (PAStar.cpp:240-250 consume_queue -> enqueue).
-// Same probe discipline as the expand kernel: each thread issues the table loads of 4 records before it looks at
-// any of them; most records are rejected right there (same key, g not better).
+// Dedupe + push of successor records: the round's local survivors and the records received from other partitions
+// (PAStar.cpp:240-250 consume_queue -> enqueue).  The record count is read from device memory, so a driver can chain
+// rounds without a host round trip.  Each thread issues the table loads of 4 records before it looks at any of them.
 template <int KEYW>
-__global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs, long long n)
+__global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
+                                                     const unsigned long long *__restrict__ n_ptr, unsigned long long n_max)
 {
     constexpr int XW = KEYW == 1 ? 3 : 4;
     constexpr int ES = KEYW == 1 ? 2 : 4;
     constexpr int PF = 4;
     SearchCtrl *c = d.ctrl;
+    if (c->error) return;
+    const long long n = (long long)min(*n_ptr, n_max);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->table_used, (unsigned long long)n); // records seen by insert kernels
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     int min_b = INT_MAX;
     const int limit = min(c->prune_limit, c->best_goal);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n; i0 += stride * PF) {
         Key<KEYW> key[PF];
-        unsigned long long gf[PF], lk[PF], lv[PF], lw[KEYW == 2 ? PF : 1];
+        unsigned long long gf[PF], lk[PF], lv[PF], lw[KEYW == 2 ? PF : 1], st[PF];
         unsigned mk[PF];
         bool live[PF];
 #pragma unroll
@@ -1004,14 +1018,17 @@ __global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ Dev
             key[j] = Key<KEYW>::zero();
             gf[j] = 0;
             mk[j] = 0;
+            st[j] = 0;
             lk[j] = lv[j] = 0;
             if (live[j]) {
                 const unsigned long long *r = recs + i * XW;
                 key[j].lo = r[0];
                 if constexpr (KEYW == 2) key[j].hi = r[1];
                 gf[j] = r[KEYW];
-                mk[j] = (unsigned)r[KEYW + 1];
+                const unsigned long long m = r[KEYW + 1];
+                mk[j] = (unsigned)m & 0xffffu;
                 if (mk[j] == 0) live[j] = false; // hole left by the sender's chunked outbox reservation
+                st[j] = (m & HINT_FLAG) ? (m >> 32) : ~0ull;
             }
             if (live[j]) {
                 bool is_goal = key[j].lo == d.goal_lo;
@@ -1020,7 +1037,8 @@ __global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ Dev
                 if ((int)(unsigned)gf[j] >= limit && !is_goal) live[j] = false;
             }
             if (live[j]) {
-                const unsigned long long *e = d.table + home_slot<KEYW>(key[j], d.kb, d.cap_mask) * ES;
+                if (st[j] == ~0ull) st[j] = home_slot<KEYW>(key[j], d.kb, d.cap_mask);
+                const unsigned long long *e = d.table + st[j] * ES;
                 ld_cg_v2(e, lk[j], lv[j]);
                 if constexpr (KEYW == 2) lw[j] = ld_cg_u64(e + 2);
             }
@@ -1029,7 +1047,7 @@ __global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ Dev
         for (int j = 0; j < PF; j++) {
             if (!live[j]) continue;
             const int gnew = (int)(unsigned)(gf[j] >> 32), f = (int)(unsigned)gf[j];
-            unsigned long long start = home_slot<KEYW>(key[j], d.kb, d.cap_mask);
+            unsigned long long start = st[j];
             if constexpr (KEYW == 1) {
                 if (lk[j] == key[j].lo + 1) {
                     if ((unsigned)gnew >= (unsigned)((~lv[j]) >> 32)) continue; // not better: drop
@@ -1048,15 +1066,28 @@ __global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ Dev
             if (cn.pushed != before) min_b = min(min_b, f - c->f0);
         }
     }
-    // A node from another partition may have a lower f than anything open here (or this partition's open list may
-    // have run empty): pull the select cursor back so the next round sees it.
+    // A node may have a lower f than anything open here (it came from another partition, or this partition's open
+    // list ran empty): pull the select cursor back so the next round sees it.
     for (int o = 16; o; o >>= 1) min_b = min(min_b, __shfl_down_sync(0xffffffffu, min_b, o));
     if ((threadIdx.x & 31) == 0 && min_b != INT_MAX) atomicMin(&c->cursor, max(min_b, 0));
-    const unsigned long long inserted = cn.inserted, pushed = cn.pushed, reopen = cn.reopen;
-    if (inserted) atomicAdd(&c->inserted, inserted);
-    if (pushed) atomicAdd(&c->pushed, pushed);
-    if (reopen) atomicAdd(&c->reopen, reopen);
+    unsigned v[3] = {cn.inserted, cn.pushed, cn.reopen};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        for (int o = 16; o; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) {
+        if (v[0]) atomicAdd(&c->inserted, (unsigned long long)v[0]);
+        if (v[1]) atomicAdd(&c->pushed, (unsigned long long)v[1]);
+        if (v[2]) atomicAdd(&c->reopen, (unsigned long long)v[2]);
+    }
 }
+
+// P2P mode: tell every owner how many records this partition stored into its inbox this round.
+__global__ void publish_counts_kernel(const __grid_constant__ DevSearch d)
+{
+    const int dst = threadIdx.x;
+    if (dst < d.n_parts && d.peer_counts[dst]) d.peer_counts[dst][d.part] = d.outbox_count[dst];
+}
+
 
 // Seed: insert the start node (Sequences::get_initial_node, Sequences.cpp:70-77; PAStar.cpp:153).
 template <int KEYW>
@@ -1267,28 +1298,36 @@ DevSearch dev_search(const pg_ctx *ctx)
     d.outbox_count = s->d_outbox_count;
     d.outbox_cap = s->outbox_cap;
     d.p2p = s->p2p ? 1 : 0;
-    for (int i = 0; i < 16; i++) d.peer_inbox[i] = (char *)s->peer_inbox[i];
+    // P2P mode: this round's half of the double-buffered inboxes / count arrays
+    const size_t half = (size_t)s->cfg.n_parts * s->outbox_cap * s->xrec;
+    for (int i = 0; i < 16; i++) {
+        d.peer_inbox[i] = s->peer_inbox[i] ? (char *)s->peer_inbox[i] + (size_t)s->p2p_buf * half : nullptr;
+        d.peer_counts[i] = s->peer_counts[i] ? s->peer_counts[i] + (size_t)s->p2p_buf * s->cfg.n_parts : nullptr;
+    }
+    d.live = s->d_live;
+    d.surv = s->d_surv;
+    d.surv_cap = s->surv_cap;
     return d;
 }
 
-template <int N, int KEYW>
+template <int N, int KEYW, bool MULTI>
 int launch_expand_round(pg_ctx *ctx, cudaStream_t st)
 {
     using C = ExpCfg<N>;
-    using Q = SlowQ<KEYW>;
     SearchState *s = ctx->search;
     constexpr int GROUPS = 256 / C::LP;
-    const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + 8 * (KEYW + 1) * 256 + 8 * 8 * Q::CAP * Q::IW +
-                        4 * 1024 + sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
+    constexpr int XW = KEYW == 1 ? 3 : 4;
+    const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + 8 * 8 * RING_CAP * XW +
+                        sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
     static int occ = 0;
     if (!occ) {
-        PG_CUDA(ctx, cudaFuncSetAttribute(search_expand_kernel<N, KEYW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_expand_kernel<N, KEYW>, 256, smem));
+        PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, MULTI>, 256, smem));
         if (occ < 1) occ = 1;
     }
-    // persistent grid: resident CTAs per SM x SM count, capped by the tiles of a full batch
+    // persistent grid: resident CTAs per SM x SM count, capped by the parent groups of a full batch
     long long grid = (long long)ctx->sm_count * occ;
-    const long long want = (s->batch_target + 255) / 256;
+    const long long want = (s->batch_target + GROUPS - 1) / GROUPS;
     if (grid > want) grid = std::max<long long>(1, want);
     OwnerArgs oa;
     oa.type = ctx->dp.hash_type;
@@ -1300,7 +1339,7 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st)
         oa.sh[m] = bit < ctx->dp.key_bits ? coord * ctx->dp.key_bits + bit : -1;
     }
     oa.nb = std::min(8, ilog2i(std::max(1, s->cfg.n_parts)) + 2);
-    search_expand_kernel<N, KEYW><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, dev_search(ctx), oa);
+    expand_probe_kernel<N, KEYW, MULTI><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, dev_search(ctx), oa);
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
 }
@@ -1308,10 +1347,11 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st)
 template <int KEYW>
 int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st)
 {
+    const bool multi = ctx->search->cfg.n_parts > 1;
     switch (ctx->n) {
 #define CASE(X) \
     case X:     \
-        return launch_expand_round<X, KEYW>(ctx, st);
+        return multi ? launch_expand_round<X, KEYW, true>(ctx, st) : launch_expand_round<X, KEYW, false>(ctx, st);
         CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(14) CASE(16)
 #undef CASE
     }
@@ -1330,18 +1370,45 @@ int prof_event(pg_ctx *ctx)
     return PG_OK;
 }
 
+constexpr size_t PROF_PER_ROUND = 5; // before select, claim, expand, insert, after insert
+
 int prof_harvest(pg_ctx *ctx) // after a stream synchronise
 {
     SearchState *s = ctx->search;
-    for (size_t i = 0; i + 2 < s->prof_used; i += 3) {
-        float a = 0, b = 0;
-        PG_CUDA(ctx, cudaEventElapsedTime(&a, s->prof_ev[i], s->prof_ev[i + 1]));
-        PG_CUDA(ctx, cudaEventElapsedTime(&b, s->prof_ev[i + 1], s->prof_ev[i + 2]));
-        s->select_ms += a;
-        s->expand_ms += b;
+    for (size_t i = 0; i + PROF_PER_ROUND <= s->prof_used; i += PROF_PER_ROUND) {
+        float t[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; k++) PG_CUDA(ctx, cudaEventElapsedTime(&t[k], s->prof_ev[i + k], s->prof_ev[i + k + 1]));
+        s->select_ms += t[0];
+        s->claim_ms += t[1];
+        s->expand_ms += t[2];
+        s->insert_ms += t[3];
     }
     s->prof_used = 0;
     return PG_OK;
+}
+
+// records at `recs`, their count in device memory at n_ptr (at most n_max)
+int launch_insert(pg_ctx *ctx, const void *recs, const unsigned long long *n_ptr, unsigned long long n_max)
+{
+    SearchState *s = ctx->search;
+    if (n_max == 0) return PG_OK;
+    const long long grid = std::min<long long>((long long)((n_max + 1023) / 1024), (long long)ctx->sm_count * 8);
+    if (s->keyw == 1)
+        insert_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max);
+    else
+        insert_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max);
+    PG_CUDA(ctx, cudaGetLastError());
+    return PG_OK;
+}
+
+// host-known counts go through a small device array (pinned staging is overkill: 64 values, once per call)
+int launch_insert_host_count(pg_ctx *ctx, const void *recs, unsigned long long n, int which)
+{
+    SearchState *s = ctx->search;
+    if (n == 0) return PG_OK;
+    unsigned long long *slot = s->d_host_counts + which;
+    PG_CUDA(ctx, cudaMemcpyAsync(slot, &s->h_host_counts[which], 8, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_insert(ctx, recs, slot, n);
 }
 
 int launch_round(pg_ctx *ctx, int f_limit)
@@ -1352,9 +1419,24 @@ int launch_round(pg_ctx *ctx, int f_limit)
     select_kernel<<<1, SELECT_THREADS, 0, ctx->stream>>>(dev_search(ctx), (long long)s->batch_target, f_limit);
     PG_CUDA(ctx, cudaGetLastError());
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
+    {
+        const long long grid = std::min<long long>((s->batch_target + 255) / 256, (long long)ctx->sm_count * 8);
+        if (s->keyw == 1)
+            claim_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx));
+        else
+            claim_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx));
+        PG_CUDA(ctx, cudaGetLastError());
+    }
+    if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
     if (rc != PG_OK) return rc;
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
+    if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
+    if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
+    if (s->p2p && s->peer_counts[0]) {
+        publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx));
+        PG_CUDA(ctx, cudaGetLastError());
+    }
     s->rounds++;
     return PG_OK;
 }
@@ -1396,8 +1478,11 @@ void fill_counters(const SearchState *s, pg_result *r)
     r->kernel_ms = s->kernel_ms;
     r->expand_ms = s->expand_ms;
     r->select_ms = s->select_ms;
+    r->survivors = (int64_t)c->table_used;
+    r->claim_ms = s->claim_ms;
+    r->insert_ms = s->insert_ms;
 #ifdef PG_PHASE_TIMING
-    fprintf(stderr, "phase warp-cycles: barrier %llu claim %llu prepare %llu pass1 %llu pass2 %llu drain %llu\n", c->phase[0], c->phase[1], c->phase[2], c->phase[3], c->phase[4], c->phase[5]);
+    fprintf(stderr, "expand phase warp-cycles: prepare %llu pass1 %llu pass2 %llu tail %llu\n", c->phase[2], c->phase[3], c->phase[4], c->phase[5]);
 #endif
 }
 
@@ -1418,6 +1503,9 @@ void pg_search_free(pg_ctx *ctx)
     cudaFree(s->d_trace);
     cudaFree(s->d_outbox);
     cudaFree(s->d_outbox_count);
+    cudaFree(s->d_live);
+    cudaFree(s->d_surv);
+    cudaFree(s->d_host_counts);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     if (s->h_outbox_count) cudaFreeHost(s->h_outbox_count);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -1516,6 +1604,14 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     }
     PG_CUDA(ctx, cudaEventCreate(&s->ev0));
     PG_CUDA(ctx, cudaEventCreate(&s->ev1));
+    {
+        // live parents: at most one per popped entry; survivors: at most every successor of every live parent
+        const uint64_t S = (1ull << ctx->n) - 1;
+        PG_CUDA(ctx, cudaMalloc(&s->d_live, (size_t)(s->batch_target + UNIT) * (s->keyw + 1) * 8));
+        s->surv_cap = (uint64_t)(s->batch_target + UNIT) * S + 64;
+        PG_CUDA(ctx, cudaMalloc(&s->d_surv, (size_t)s->surv_cap * s->xrec));
+        PG_CUDA(ctx, cudaMalloc(&s->d_host_counts, 8 * 64));
+    }
     if (cfg->n_parts > 1) {
         // worst case every successor of a full batch goes to one destination
         const uint64_t S = (1ull << ctx->n) - 1;
@@ -1557,11 +1653,26 @@ extern "C" int pg_search_round(pg_ctx *ctx, int32_t f_limit)
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     SearchState *s = ctx->search;
     if (s->cfg.n_parts > 1 && s->cfg.reserved == 1 && !s->p2p) return pg_fail(ctx, PG_ERR_STATE, "P2P mode requested but pg_search_set_peers has not run");
-    if (s->cfg.n_parts > 1) PG_CUDA(ctx, cudaMemsetAsync(s->d_outbox_count, 0, 8 * 64, ctx->stream));
     int rc = launch_round(ctx, f_limit);
     if (rc != PG_OK) return rc;
     if (s->cfg.n_parts > 1)
         PG_CUDA(ctx, cudaMemcpyAsync(s->h_outbox_count, s->d_outbox_count, 8 * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_ctrl(ctx);
+}
+
+extern "C" int pg_search_round_async(pg_ctx *ctx, int32_t f_limit)
+{
+    if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SearchState *s = ctx->search;
+    if (s->cfg.n_parts > 1 && s->cfg.reserved == 1 && !s->p2p) return pg_fail(ctx, PG_ERR_STATE, "P2P mode requested but pg_search_set_peers has not run");
+    return launch_round(ctx, f_limit);
+}
+
+extern "C" int pg_search_sync(pg_ctx *ctx)
+{
+    if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
     return sync_ctrl(ctx);
 }
 
@@ -1594,6 +1705,34 @@ extern "C" int pg_search_set_peers(pg_ctx *ctx, void *const *peer_inbox, int n)
     return PG_OK;
 }
 
+extern "C" int pg_search_set_peer_counts(pg_ctx *ctx, void *const *peer_counts, int n, int nbuf)
+{
+    if (!ctx || !ctx->search || !peer_counts) return PG_ERR_ARG;
+    SearchState *s = ctx->search;
+    if (n != s->cfg.n_parts || n > 16 || nbuf < 1 || nbuf > 2) return pg_fail(ctx, PG_ERR_ARG, "pg_search_set_peer_counts: one count array per partition, 1 or 2 buffers");
+    for (int i = 0; i < n; i++) s->peer_counts[i] = (unsigned long long *)peer_counts[i];
+    s->p2p_nbuf = nbuf;
+    s->p2p_buf = 0;
+    return PG_OK;
+}
+
+extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
+{
+    if (!ctx || !ctx->search) return PG_ERR_ARG;
+    SearchState *s = ctx->search;
+    if (!s->p2p || !s->peer_counts[s->cfg.part]) return pg_fail(ctx, PG_ERR_STATE, "pg_search_insert_inbox_async needs pg_search_set_peers and pg_search_set_peer_counts");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const DevSearch d = dev_search(ctx);
+    const size_t region = (size_t)s->outbox_cap * s->xrec;
+    for (int src = 0; src < s->cfg.n_parts; src++) {
+        if (src == s->cfg.part) continue;
+        int rc = launch_insert(ctx, d.peer_inbox[s->cfg.part] + (size_t)src * region, d.peer_counts[s->cfg.part] + src, s->outbox_cap);
+        if (rc != PG_OK) return rc;
+    }
+    s->p2p_buf = (s->p2p_buf + 1) % s->p2p_nbuf;
+    return PG_OK;
+}
+
 extern "C" int64_t pg_search_outbox_capacity(const pg_ctx *ctx)
 {
     return ctx && ctx->search ? (int64_t)ctx->search->outbox_cap : 0;
@@ -1608,18 +1747,14 @@ extern "C" int pg_search_outbox_counts_dev(pg_ctx *ctx, void **d_counts)
 
 extern "C" int pg_search_insert_segments_dev(pg_ctx *ctx, const void *base, int64_t stride_bytes, const int64_t *counts, int n)
 {
-    if (!ctx || !ctx->search || !base || !counts || n < 0) return PG_ERR_ARG;
+    if (!ctx || !ctx->search || !base || !counts || n < 0 || n > 64) return PG_ERR_ARG;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     SearchState *s = ctx->search;
     for (int i = 0; i < n; i++) {
         if (counts[i] <= 0) continue;
-        const unsigned long long *recs = (const unsigned long long *)((const char *)base + (size_t)i * stride_bytes);
-        const long long grid = std::min<long long>((counts[i] + 255) / 256, (long long)ctx->sm_count * 8);
-        if (s->keyw == 1)
-            insert_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), recs, (long long)counts[i]);
-        else
-            insert_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), recs, (long long)counts[i]);
-        PG_CUDA(ctx, cudaGetLastError());
+        s->h_host_counts[i] = (unsigned long long)counts[i];
+        int rc = launch_insert_host_count(ctx, (const char *)base + (size_t)i * stride_bytes, (unsigned long long)counts[i], i);
+        if (rc != PG_OK) return rc;
     }
     return sync_ctrl(ctx);
 }
@@ -1640,12 +1775,9 @@ extern "C" int pg_search_insert_dev(pg_ctx *ctx, const void *d_records, int64_t 
     if (count == 0) return PG_OK;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     SearchState *s = ctx->search;
-    const long long grid = std::min<long long>((count + 255) / 256, (long long)ctx->sm_count * 8);
-    if (s->keyw == 1)
-        insert_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)d_records, (long long)count);
-    else
-        insert_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)d_records, (long long)count);
-    PG_CUDA(ctx, cudaGetLastError());
+    s->h_host_counts[63] = (unsigned long long)count;
+    int rc = launch_insert_host_count(ctx, d_records, (unsigned long long)count, 63);
+    if (rc != PG_OK) return rc;
     return sync_ctrl(ctx);
 }
 
