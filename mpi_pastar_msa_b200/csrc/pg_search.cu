@@ -72,7 +72,8 @@ struct SearchState {
     SearchCtrl *d_ctrl = nullptr;
     SearchCtrl *h_ctrl = nullptr; // pinned
     uint32_t *d_trace = nullptr;  // backtrace output
-    unsigned long long *d_live = nullptr;  // live parents of the round: (keyw + 1) u64 each
+    unsigned long long *d_live = nullptr;  // live parents of the round: (keyw + 1) arrays of live_cap u64
+    uint64_t live_cap = 0;
     unsigned long long *d_surv = nullptr;  // local survivors of the round: pg_xrec records
     uint64_t surv_cap = 0;
     unsigned long long *d_host_counts = nullptr; // record counts the host passes to insert launches
@@ -230,7 +231,8 @@ struct DevSearch {
     char *peer_inbox[16];
     unsigned long long *peer_counts[16];
     int p2p;
-    unsigned long long *live;     // compacted live parents of the round
+    unsigned long long *live;     // compacted live parents of the round, word-major: live[w * live_cap + i]
+    unsigned long long live_cap;
     unsigned long long *surv;     // local survivors of the round
     unsigned long long surv_cap;
 };
@@ -298,24 +300,16 @@ __device__ __forceinline__ unsigned long long *val_ptr(const DevSearch &d, unsig
     return d.table + slot * (KEYW == 1 ? 2 : 4) + (KEYW == 1 ? 1 : 2);
 }
 
-// Push a table slot on the open bucket of f.
-//   old fill < capacity : the slot is written in place
+// Push a table slot on the open bucket of f.  One atomicAdd hands out a position:
+//   old fill < capacity : the slot is written in place (the fast path; callers may issue the atomic themselves and
+//                         pass its result to bucket_place, so that several pushes are in flight per thread)
 //   old fill == capacity: this thread installs the next (twice as large) chunk
-//   old fill > capacity : an install is in flight; poll and retry
-__device__ __forceinline__ void bucket_push(const DevSearch &d, int f, uint32_t slot)
+//   old fill > capacity : an install is in flight; poll until the new head is published, then retry
+__device__ __noinline__ void bucket_place_slow(const DevSearch &d, int b, uint32_t slot, unsigned long long st)
 {
     SearchCtrl *c = d.ctrl;
-    int b = f - c->f0;
-    if (b < 0) b = 0; // cannot happen with a consistent heuristic; keep it poppable
-    if (b >= c->f_range) {
-        c->error = 3;
-        return;
-    }
     unsigned long long *bk = d.buckets + b;
     for (;;) {
-        const unsigned long long cur = ld_cg_u64(bk);
-        if (((uint32_t)cur & CNT_MASK) > (UNIT << (((uint32_t)cur >> 27) & 31u))) continue;
-        const unsigned long long st = atomicAdd(bk, 1ull);
         const uint32_t cnt = (uint32_t)st & CNT_MASK, lg = ((uint32_t)st >> 27) & 31u, off = (uint32_t)(st >> 32);
         const uint32_t capn = UNIT << lg;
         if (cnt < capn) {
@@ -340,7 +334,38 @@ __device__ __forceinline__ void bucket_push(const DevSearch &d, int f, uint32_t 
             if (nlg > d.hint[b]) d.hint[b] = nlg;
             return;
         }
+        for (;;) { // install in flight
+            const unsigned long long cur = ld_cg_u64(bk);
+            if (((uint32_t)cur & CNT_MASK) <= (UNIT << (((uint32_t)cur >> 27) & 31u))) break;
+        }
+        st = atomicAdd(bk, 1ull);
     }
+}
+// bucket index of f, or -1 (error raised) when f is beyond the bucket range
+__device__ __forceinline__ int bucket_of(const DevSearch &d, int f)
+{
+    SearchCtrl *c = d.ctrl;
+    int b = f - c->f0;
+    if (b < 0) b = 0; // cannot happen with a consistent heuristic; keep it poppable
+    if (b >= c->f_range) {
+        c->error = 3;
+        return -1;
+    }
+    return b;
+}
+__device__ __forceinline__ void bucket_place(const DevSearch &d, int b, uint32_t slot, unsigned long long st)
+{
+    const uint32_t cnt = (uint32_t)st & CNT_MASK, lg = ((uint32_t)st >> 27) & 31u, off = (uint32_t)(st >> 32);
+    if (cnt < (UNIT << lg))
+        d.pool[(size_t)off * UNIT + cnt] = slot;
+    else
+        bucket_place_slow(d, b, slot, st);
+}
+__device__ __forceinline__ void bucket_push(const DevSearch &d, int f, uint32_t slot)
+{
+    const int b = bucket_of(d, f);
+    if (b < 0) return;
+    bucket_place(d, b, slot, atomicAdd(d.buckets + b, 1ull));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -488,11 +513,13 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, lon
     }
 }
 
-// slow path for one successor: find/claim its slot starting at `slot`, install g if strictly better, push.
+// One record at a time: find/claim its slot starting at `slot`, install g if strictly better, push.
+// Returns UPS_* flags.
+enum { UPS_INSERTED = 1, UPS_PUSHED = 2, UPS_REOPEN = 4 };
 template <int KEYW>
-__device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> &key, unsigned long long slot, int gnew, int f, int mask,
-                                            Counters &cn)
+__device__ __noinline__ unsigned upsert_from(const DevSearch &d, const Key<KEYW> key, unsigned long long slot, int gnew, int f, int mask)
 {
+    unsigned flags = 0;
     constexpr int ES = KEYW == 1 ? 2 : 4;
     unsigned long long val = 0;
     bool found = false;
@@ -509,7 +536,7 @@ __device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> 
             if (k != 0) continue;
             const unsigned long long prev = atomicCAS(e, 0ull, key.lo + 1);
             if (prev == 0) {
-                cn.inserted++;
+                flags |= UPS_INSERTED;
                 val = 0;
                 found = true;
                 break;
@@ -532,7 +559,7 @@ __device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> 
             unsigned long long p0, p1;
             cas128(e, want0, want1, p0, p1);
             if (p0 == 0 && p1 == 0) {
-                cn.inserted++;
+                flags |= UPS_INSERTED;
                 val = 0;
                 found = true;
                 break;
@@ -546,20 +573,20 @@ __device__ __forceinline__ void upsert_from(const DevSearch &d, const Key<KEYW> 
     }
     if (!found) {
         d.ctrl->error = 1;
-        return;
+        return flags;
     }
     unsigned long long *vp = val_ptr<KEYW>(d, slot);
     const unsigned long long mine = ~(((unsigned long long)(unsigned)gnew << 32) | OPEN_BIT | (unsigned long long)(unsigned)mask);
     for (;;) {
         const unsigned g_old = (unsigned)((~val) >> 32); // 0xffffffff for a fresh entry
-        if ((unsigned)gnew >= g_old) return;             // PAStar.cpp:228 / PriorityList.h:109: not better, drop
+        if ((unsigned)gnew >= g_old) return flags;       // PAStar.cpp:228 / PriorityList.h:109: not better, drop
         const unsigned long long prev = atomicCAS(vp, val, mine);
         if (prev == val) break;
         val = prev;
     }
-    if (val != 0 && !((~val) & OPEN_BIT)) cn.reopen++; // was closed with a worse g: PAStar.cpp:230-231
-    cn.pushed++;
+    if (val != 0 && !((~val) & OPEN_BIT)) flags |= UPS_REOPEN; // was closed with a worse g: PAStar.cpp:230-231
     bucket_push(d, f, (uint32_t)slot);
+    return flags | UPS_PUSHED;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -643,10 +670,10 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
         if (lane == 0 && bal) wbase = atomicAdd(&c->live_n, __popc(bal));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
         if (live) {
-            unsigned long long *r = d.live + (size_t)(wbase + __popc(bal & lt)) * (KEYW + 1);
+            unsigned long long *r = d.live + (size_t)(wbase + __popc(bal & lt));
             r[0] = klo;
-            if constexpr (KEYW == 2) r[1] = khi;
-            r[KEYW] = val;
+            if constexpr (KEYW == 2) r[d.live_cap] = khi;
+            r[KEYW * d.live_cap] = val;
         }
     }
 }
@@ -768,10 +795,10 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
     int pi = blockIdx.x * GROUPS + grp;
     unsigned long long nk0 = 0, nk1 = 0, nval = 0;
     if (pi < live_n) {
-        const unsigned long long *r = d.live + (size_t)pi * (KEYW + 1);
+        const unsigned long long *r = d.live + (size_t)pi;
         nk0 = __ldg(r);
-        if constexpr (KEYW == 2) nk1 = __ldg(r + 1);
-        nval = __ldg(r + KEYW);
+        if constexpr (KEYW == 2) nk1 = __ldg(r + d.live_cap);
+        nval = __ldg(r + KEYW * d.live_cap);
     }
     for (int wfirst = blockIdx.x * GROUPS + warp * GPW; wfirst < live_n; wfirst += stride, pi += stride) {
         bool act = pi < live_n;
@@ -780,10 +807,10 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
         if constexpr (KEYW == 2) pkey.hi = nk1;
         const unsigned long long val = nval;
         if (pi + stride < live_n) { // the next parent's record travels while this one is expanded
-            const unsigned long long *r = d.live + (size_t)(pi + stride) * (KEYW + 1);
+            const unsigned long long *r = d.live + (size_t)(pi + stride);
             nk0 = __ldg(r);
-            if constexpr (KEYW == 2) nk1 = __ldg(r + 1);
-            nval = __ldg(r + KEYW);
+            if constexpr (KEYW == 2) nk1 = __ldg(r + d.live_cap);
+            nval = __ldg(r + KEYW * d.live_cap);
         }
         int pos[N];
         int goal_mask = 0;
@@ -989,15 +1016,20 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
 }
 
 // Dedupe + push of successor records: the round's local survivors and the records received from other partitions
-// (PAStar.cpp:240-250 consume_queue -> enqueue).  The record count is read from device memory, so a driver can chain
-// rounds without a host round trip.  Each thread issues the table loads of 4 records before it looks at any of them.
+// (PAStar.cpp:240-250 consume_queue -> enqueue; PAStar.cpp:219-237; PriorityList.h:104-113).  The record count is read
+// from device memory, so a driver can chain rounds without a host round trip.  Every step of the chain
+//     record -> table entry -> CAS key (new coordinate) -> CAS value (strictly better g) -> bucket atomicAdd -> pool store
+// is issued for 4 records per thread before any of its results is used, so 4 dependent chains overlap per thread.
+// What does not fit the straight line (hash collision, a CAS lost to a concurrent writer of the same entry, a bucket
+// whose chunk is full) takes the one-record-at-a-time path (upsert_from / bucket_place_slow).
 template <int KEYW>
-__global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
-                                                     const unsigned long long *__restrict__ n_ptr, unsigned long long n_max)
+__global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
+                                                        const unsigned long long *__restrict__ n_ptr, unsigned long long n_max)
 {
     constexpr int XW = KEYW == 1 ? 3 : 4;
     constexpr int ES = KEYW == 1 ? 2 : 4;
     constexpr int PF = 4;
+    enum { DONE = 0, KEY = 1, VAL = 2, PUSH = 3, WALK = 4 };
     SearchCtrl *c = d.ctrl;
     if (c->error) return;
     const long long n = (long long)min(*n_ptr, n_max);
@@ -1008,62 +1040,126 @@ __global__ void __launch_bounds__(256) insert_kernel(const __grid_constant__ Dev
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n; i0 += stride * PF) {
         Key<KEYW> key[PF];
-        unsigned long long gf[PF], lk[PF], lv[PF], lw[KEYW == 2 ? PF : 1], st[PF];
+        unsigned long long gf[PF], lk[PF], lv[PF], lw[KEYW == 2 ? PF : 1];
+        uint32_t st[PF];
         unsigned mk[PF];
-        bool live[PF];
+        int state[PF];
+        // ---- records
 #pragma unroll
         for (int j = 0; j < PF; j++) {
             const long long i = i0 + j * stride;
-            live[j] = i < n;
+            state[j] = DONE;
             key[j] = Key<KEYW>::zero();
             gf[j] = 0;
             mk[j] = 0;
             st[j] = 0;
             lk[j] = lv[j] = 0;
-            if (live[j]) {
+            if (i < n) {
                 const unsigned long long *r = recs + i * XW;
-                key[j].lo = r[0];
-                if constexpr (KEYW == 2) key[j].hi = r[1];
-                gf[j] = r[KEYW];
-                const unsigned long long m = r[KEYW + 1];
+                key[j].lo = __ldcs(r);
+                if constexpr (KEYW == 2) key[j].hi = __ldcs(r + 1);
+                gf[j] = __ldcs(r + KEYW);
+                const unsigned long long m = __ldcs(r + KEYW + 1);
                 mk[j] = (unsigned)m & 0xffffu;
-                if (mk[j] == 0) live[j] = false; // hole left by the sender's chunked outbox reservation
-                st[j] = (m & HINT_FLAG) ? (m >> 32) : ~0ull;
-            }
-            if (live[j]) {
-                bool is_goal = key[j].lo == d.goal_lo;
-                if constexpr (KEYW == 2) is_goal = is_goal && key[j].hi == d.goal_hi;
-                if (is_goal) atomicMin(&c->best_goal, (int)(unsigned)(gf[j] >> 32));
-                if ((int)(unsigned)gf[j] >= limit && !is_goal) live[j] = false;
-            }
-            if (live[j]) {
-                if (st[j] == ~0ull) st[j] = home_slot<KEYW>(key[j], d.kb, d.cap_mask);
-                const unsigned long long *e = d.table + st[j] * ES;
-                ld_cg_v2(e, lk[j], lv[j]);
-                if constexpr (KEYW == 2) lw[j] = ld_cg_u64(e + 2);
+                st[j] = (uint32_t)(m >> 32);
+                state[j] = mk[j] == 0 ? DONE : ((m & HINT_FLAG) ? VAL : KEY); // move mask 0: hole left by the sender's chunked outbox
             }
         }
+        // ---- table entries
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            if (!live[j]) continue;
-            const int gnew = (int)(unsigned)(gf[j] >> 32), f = (int)(unsigned)gf[j];
-            unsigned long long start = st[j];
+            if (state[j] == DONE) continue;
+            bool is_goal = key[j].lo == d.goal_lo;
+            if constexpr (KEYW == 2) is_goal = is_goal && key[j].hi == d.goal_hi;
+            if (is_goal) atomicMin(&c->best_goal, (int)(unsigned)(gf[j] >> 32));
+            if ((int)(unsigned)gf[j] >= limit && !is_goal) {
+                state[j] = DONE;
+                continue;
+            }
+            if (state[j] == KEY) st[j] = (uint32_t)home_slot<KEYW>(key[j], d.kb, d.cap_mask); // no slot hint in the record
+            const unsigned long long *e = d.table + (size_t)st[j] * ES;
+            ld_cg_v2(e, lk[j], lv[j]);
+            if constexpr (KEYW == 2) lw[j] = ld_cg_u64(e + 2);
+        }
+        // ---- classify; CAS the key of the empty slots
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            if (state[j] == DONE) continue;
+            unsigned long long *e = d.table + (size_t)st[j] * ES;
+            const unsigned gnew = (unsigned)(gf[j] >> 32);
             if constexpr (KEYW == 1) {
                 if (lk[j] == key[j].lo + 1) {
-                    if ((unsigned)gnew >= (unsigned)((~lv[j]) >> 32)) continue; // not better: drop
-                } else if (lk[j] != 0) {
-                    start = next_slot<KEYW>(start, d.cap_mask);
+                    state[j] = gnew < (unsigned)((~lv[j]) >> 32) ? VAL : DONE; // not better: drop
+                } else if (lk[j] == 0) {
+                    state[j] = KEY;
+                    lk[j] = atomicCAS(e, 0ull, key[j].lo + 1);
+                } else {
+                    state[j] = WALK;
+                    st[j] = (uint32_t)next_slot<KEYW>(st[j], d.cap_mask);
                 }
             } else {
                 if (lk[j] == key[j].lo && lv[j] == (key[j].hi | (1ull << 63))) {
-                    if ((unsigned)gnew >= (unsigned)((~lw[j]) >> 32)) continue;
-                } else if (lk[j] != 0 || lv[j] != 0) {
-                    start = next_slot<KEYW>(start, d.cap_mask);
+                    state[j] = gnew < (unsigned)((~lw[j]) >> 32) ? VAL : DONE;
+                    lv[j] = lw[j];
+                } else if (lk[j] == 0 && lv[j] == 0) {
+                    state[j] = KEY;
+                    cas128(e, key[j].lo, key[j].hi | (1ull << 63), lk[j], lv[j]);
+                } else {
+                    state[j] = WALK;
+                    st[j] = (uint32_t)next_slot<KEYW>(st[j], d.cap_mask);
                 }
             }
-            const unsigned before = cn.pushed;
-            upsert_from<KEYW>(d, key[j], start, gnew, f, (int)mk[j], cn);
-            if (cn.pushed != before) min_b = min(min_b, f - c->f0);
+        }
+        // ---- CAS the value where this record is strictly better (lv = the value the CAS expects)
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            if (state[j] == KEY) {
+                const bool won = KEYW == 1 ? lk[j] == 0 : (lk[j] == 0 && lv[j] == 0);
+                if (won) {
+                    cn.inserted++;
+                    lv[j] = 0;
+                    state[j] = VAL;
+                } else {
+                    state[j] = WALK; // lost the slot to a concurrent insert (of this key or another): re-read it
+                }
+            }
+            if (state[j] == VAL) {
+                const unsigned long long mine = ~((gf[j] & 0xffffffff00000000ull) | OPEN_BIT | (unsigned long long)mk[j]);
+                lk[j] = atomicCAS(val_ptr<KEYW>(d, st[j]), lv[j], mine);
+            }
+        }
+        // ---- bucket positions for the records that went in
+        int bk[PF];
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            bk[j] = -1;
+            if (state[j] != VAL) continue;
+            if (lk[j] == lv[j]) {
+                if (lv[j] != 0 && !((~lv[j]) & OPEN_BIT)) cn.reopen++; // was closed with a worse g: PAStar.cpp:230-231
+                cn.pushed++;
+                bk[j] = bucket_of(d, (int)(unsigned)gf[j]);
+                state[j] = bk[j] >= 0 ? PUSH : DONE;
+                if (bk[j] >= 0) {
+                    min_b = min(min_b, bk[j]);
+                    lk[j] = atomicAdd(d.buckets + bk[j], 1ull);
+                }
+            } else {
+                // a concurrent writer changed the value: still better than what is there now?
+                state[j] = (unsigned)(gf[j] >> 32) < (unsigned)((~lk[j]) >> 32) ? WALK : DONE;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PF; j++)
+            if (state[j] == PUSH) bucket_place(d, bk[j], st[j], lk[j]);
+        // ---- everything else, one at a time
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            if (state[j] != WALK) continue;
+            const unsigned fl = upsert_from<KEYW>(d, key[j], st[j], (int)(unsigned)(gf[j] >> 32), (int)(unsigned)gf[j], (int)mk[j]);
+            cn.inserted += fl & UPS_INSERTED;
+            cn.pushed += (fl >> 1) & 1u;
+            cn.reopen += (fl >> 2) & 1u;
+            if (fl & UPS_PUSHED) min_b = min(min_b, (int)(unsigned)gf[j] - c->f0);
         }
     }
     // A node may have a lower f than anything open here (it came from another partition, or this partition's open
@@ -1305,6 +1401,7 @@ DevSearch dev_search(const pg_ctx *ctx)
         d.peer_counts[i] = s->peer_counts[i] ? s->peer_counts[i] + (size_t)s->p2p_buf * s->cfg.n_parts : nullptr;
     }
     d.live = s->d_live;
+    d.live_cap = s->live_cap;
     d.surv = s->d_surv;
     d.surv_cap = s->surv_cap;
     return d;
@@ -1607,7 +1704,8 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     {
         // live parents: at most one per popped entry; survivors: at most every successor of every live parent
         const uint64_t S = (1ull << ctx->n) - 1;
-        PG_CUDA(ctx, cudaMalloc(&s->d_live, (size_t)(s->batch_target + UNIT) * (s->keyw + 1) * 8));
+        s->live_cap = (uint64_t)s->batch_target + UNIT;
+        PG_CUDA(ctx, cudaMalloc(&s->d_live, (size_t)s->live_cap * (s->keyw + 1) * 8));
         s->surv_cap = (uint64_t)(s->batch_target + UNIT) * S + 64;
         PG_CUDA(ctx, cudaMalloc(&s->d_surv, (size_t)s->surv_cap * s->xrec));
         PG_CUDA(ctx, cudaMalloc(&s->d_host_counts, 8 * 64));
