@@ -202,33 +202,43 @@ def run_ours(args, rank, world):
         from mpi_pastar_msa_b200.dist import CudaEngine, CudaEngineP2P, PartitionedSearch
         G.configure_hash("FZORDER", 12)
         try:  # fused expansion + exchange over peer-mapped inboxes; NCCL all-to-all if symmetric memory is unavailable
-            eng = CudaEngineP2P(G, world, rank, dist, cap, batch)
-            extra["exchange"] = "p2p stores into peer-mapped inboxes (NVLink), counts by all_gather"
+            if os.environ.get("PG_P2P", "1") == "0":
+                raise RuntimeError("PG_P2P=0")
+            fwd = os.environ.get("PG_FWD", "1") == "1"
+            eng = CudaEngineP2P(G, world, rank, dist, cap, batch, forward=fwd)
+            extra["exchange"] = ("device-driven parent forwarding: the claim kernel stores each live parent into the peer-mapped inbox (NVLink) of "
+                                 "every partition owning one of its successors; counts published by a device kernel, one symmetric-memory barrier per round"
+                                 if fwd else
+                                 "device-driven: p2p stores of successor records into peer-mapped inboxes (NVLink) from the expand kernel, counts "
+                                 "published by a device kernel, one symmetric-memory barrier per round")
         except Exception as ex:
             eng = CudaEngine(G, world, rank, cap, batch)
             extra["exchange"] = "nccl all_to_all_single (p2p unavailable: %r)" % (ex,)
         drv = PartitionedSearch(eng, dist, seqs, lambda pos: int(G.owner(np.array(pos, dtype=np.uint16), world)[0]))
-        launches_per_step = 3 + (world - 1)  # select + fused expand + one insert per source + status select
+        launches_per_step = 5 + (world - 1)  # select, claim, expand/probe, insert (local), publish counts + one insert per source
+        chained = getattr(eng, "async_rounds", False)  # device-driven rounds: one status exchange per call, not per round
         ramp = 0
         while True:
-            _, _, tot0 = drv.step()
-            ramp += 1
-            if ramp >= 8:
-                _, _, tot1 = drv.step()
-                ramp += 1
-                if tot1[2] - tot0[2] >= world * batch or ramp > 4000:
-                    break
-        for _ in range(W):
-            drv.step()
+            _, _, tot0 = drv.step(rounds=8 if chained else 1)
+            _, _, tot1 = drv.step(rounds=8 if chained else 1)
+            ramp += 16 if chained else 2
+            if tot1[2] - tot0[2] >= (8 if chained else 1) * world * batch or ramp > 4000:
+                break
+        drv.step(rounds=W)
         _, _, tot0 = drv.step()
+        G.search_profile(True)
+        pc0 = G.search_status()[2]
         sampler = ClockSampler(local)
         sampler.start()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
         sent0 = drv.bytes_sent
-        for _ in range(K):
-            _, _, tot1 = drv.step()
+        e0.record(stream)
+        if chained:
+            _, _, tot1 = drv.step(rounds=K)
+        else:
+            for _ in range(K):
+                _, _, tot1 = drv.step()
         e1.record(stream)
         barrier()
         sampler.stop_flag = True
@@ -239,6 +249,10 @@ def run_ours(args, rank, world):
         total_exp = tot1[0] - tot0[0]
         d = {"expansions": total_exp, "generated": tot1[1] - tot0[1], "pops": tot1[2] - tot0[2]}
         extra["nvlink_bytes_per_step_per_gpu"] = (drv.bytes_sent - sent0) / K
+        pc1 = G.search_status()[2]
+        G.search_profile(False)
+        extra["rank0_kernel_ms_per_step"] = {k: (pc1[k] - pc0[k]) / K for k in ("select_ms", "claim_ms", "expand_ms", "insert_ms", "inbox_ms")}
+        extra["rank0_records_inserted_per_step"] = (pc1["survivors"] - pc0["survivors"]) / K
         expand_ms = select_ms = None
         eng.end()
 

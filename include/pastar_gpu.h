@@ -126,7 +126,7 @@ typedef struct {
     int64_t batch_target;   /* frontier nodes popped per round (whole f-buckets, at least one); 0 = auto */
     int64_t max_expansions; /* > 0: stop after this many expansions (budgeted run, not optimal)  */
     int32_t rounds_per_sync;/* rounds launched between host checks; 0 = auto                     */
-    int32_t reserved;       /* 1 = P2P mode: see pg_search_set_peers                              */
+    int32_t reserved;       /* 1 = P2P successor records, 2 = P2P parent forwarding: see pg_search_set_peers */
 } pg_search_config;
 
 typedef struct {
@@ -149,6 +149,7 @@ typedef struct {
     double claim_ms;        /* ... of the claim kernel (closed-bit claim + compaction of live parents) */
     double insert_ms;       /* ... of the insert kernel over the round's local survivors          */
     int64_t survivors;      /* records run through the insert kernel (local survivors + received records) */
+    double inbox_ms;        /* ... of the insert kernels over the records received from other partitions (P2P mode) */
 } pg_result;
 
 /* Replaces PAStar<N>::pa_star (pastar/PAStar.cpp:626-673) on ONE GPU
@@ -188,6 +189,12 @@ int pg_search_set_peer_counts(pg_ctx *ctx, void *const *peer_counts, int n, int 
 /* pg_search_round without the host synchronisation (launches only); pair with pg_search_sync. */
 int pg_search_round_async(pg_ctx *ctx, int32_t f_limit);
 int pg_search_insert_inbox_async(pg_ctx *ctx);
+/* bytes one source partition may write into one inbox per buffer: the symmetric allocation the driver makes is
+ * nbuf x n_parts x this.  pg_search_config.reserved selects what crosses NVLink: 1 = successor records
+ * (pg_xrec), stored by the expand kernel; 2 = parent forwarding: the claim kernel sends each live parent
+ * (key + g + parenti, 16 or 24 bytes) to every partition that owns one of its successors, and that partition
+ * generates them itself - about fifty times less traffic for the same result. */
+int64_t pg_search_region_bytes(const pg_ctx *ctx);
 /* wait for the launched rounds; reports capacity errors like pg_search_round */
 int pg_search_sync(pg_ctx *ctx);
 int64_t pg_search_outbox_capacity(const pg_ctx *ctx);

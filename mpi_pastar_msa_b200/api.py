@@ -39,7 +39,7 @@ class Result(C.Structure):
                 ("closed_size", C.c_int64), ("rounds", C.c_int64), ("probed", C.c_int64), ("pushed", C.c_int64),
                 ("inserted", C.c_int64), ("seconds", C.c_double), ("kernel_ms", C.c_double), ("expand_ms", C.c_double),
                 ("select_ms", C.c_double), ("claim_ms", C.c_double), ("insert_ms", C.c_double),
-                ("survivors", C.c_int64)]
+                ("survivors", C.c_int64), ("inbox_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -92,6 +92,7 @@ def load_library():
         "pg_search_round_async": ([vp, C.c_int32], i32),
         "pg_search_insert_inbox_async": ([vp], i32),
         "pg_search_sync": ([vp], i32),
+        "pg_search_region_bytes": ([vp], i64),
         "pg_search_outbox_capacity": ([vp], i64),
         "pg_search_outbox_counts_dev": ([vp, C.POINTER(vp)], i32),
         "pg_search_insert_segments_dev": ([vp, vp, i64, C.POINTER(i64), i32], i32),
@@ -108,7 +109,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -306,7 +307,9 @@ class PastarGPU:
 
     # step-wise (multi-GPU drivers)
     def search_begin(self, n_parts=1, part=0, table_capacity=0, batch_target=0, p2p=False):
-        cfg = SearchConfig(n_parts, part, table_capacity, batch_target, 0, 0, 1 if p2p else 0)
+        """p2p: False/0 = local outboxes (NCCL all-to-all by the driver), True/1 = successor records stored into the
+        owners' peer-mapped inboxes, 2 = parent forwarding over the peer-mapped inboxes."""
+        cfg = SearchConfig(n_parts, part, table_capacity, batch_target, 0, 0, int(p2p))
         self._ck(self.L.pg_search_begin(self.h, C.byref(cfg)))
 
     def search_set_peers(self, ptrs):
@@ -325,6 +328,9 @@ class PastarGPU:
 
     def search_sync(self):
         self._ck(self.L.pg_search_sync(self.h))
+
+    def search_region_bytes(self):
+        return int(self.L.pg_search_region_bytes(self.h))
 
     def search_outbox_capacity(self):
         return int(self.L.pg_search_outbox_capacity(self.h))

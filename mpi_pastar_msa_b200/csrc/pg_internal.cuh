@@ -51,8 +51,7 @@ struct SearchCtrl {          // lives in device memory; mirrored to pinned host 
     uint32_t pad0;
     unsigned long long pops, expansions, generated, reopen, inserted, pushed, pruned, table_used; // table_used: records seen by insert kernels
     unsigned long long surv_n;   // local survivors of the current round (records in SearchState::d_surv)
-    int32_t live_n;              // live parents of the current round (after the closed-bit claim)
-    int32_t pad1;
+    unsigned long long live_n;   // live parents of the current round (after the closed-bit claim)
     unsigned long long phase[8]; // PG_PHASE_TIMING builds: warp-cycles per phase of the expand kernel
 };
 

@@ -90,13 +90,17 @@ struct SearchState {
     unsigned long long *peer_counts[16] = {nullptr}; // P2P mode: every partition's uint64[nbuf][n_parts] "records from source s"
     int p2p_nbuf = 1, p2p_buf = 0;                   // double-buffered inboxes: one cross-GPU barrier per round is enough
     bool p2p = false;
+    bool forward = false;      // P2P parent forwarding (pg_search_config.reserved == 2)
+    size_t region_bytes = 0;   // bytes one source may write into one inbox (per buffer)
     int xrec = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-launch timing: event triples (before select, between, after expand), harvested at every sync
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
-    double expand_ms = 0, select_ms = 0, claim_ms = 0, insert_ms = 0;
+    double expand_ms = 0, select_ms = 0, claim_ms = 0, insert_ms = 0, inbox_ms = 0;
+    std::vector<cudaEvent_t> prof_ev2; // pairs around the inbox inserts
+    size_t prof_used2 = 0;
     double kernel_ms = 0;
     int64_t rounds = 0;
     bool active = false;
@@ -612,17 +616,80 @@ __device__ __noinline__ unsigned upsert_from(const DevSearch &d, const Key<KEYW>
 #define PH_MARK(idx) do { } while (0)
 #endif
 
+// Owner hash arguments.  Z-order hashes: bit m of the owner word is bit `bit[m]` of coordinate `co[m]`
+// (co < 0: beyond the coordinate width, reads 0); the word is reduced mod n_parts through a 256-entry table.
 struct OwnerArgs {
     int type, shift, nb;
-    int sh[8];
+    int co[8], bit[8];
+    int nfc;            // distinct coordinates the owner word reads ...
+    int fc[8], fcm[8];  // ... and, per coordinate, the mask of owner-word bits tied to it
 };
+
+// The round's parents as the expand kernel sees them: one or more word-major regions ((KEYW + 1) arrays of `cap`
+// u64: key words, then ~value) whose record counts live in device memory.  own = 0: parents forwarded by other
+// partitions (their owners count the expansion).
+struct ParentSrc {
+    const unsigned long long *base[16];
+    const unsigned long long *count[16];
+    unsigned long long cap;
+    int n, own;
+};
+
+// Partitions (bit set) that own at least one successor of the node `key`; `part` itself is not reported.
+template <int KEYW>
+__device__ __forceinline__ unsigned successor_owners(const DevProblem &p, const OwnerArgs &oa, const Key<KEYW> &key, int n_parts, int part)
+{
+    const unsigned fmask = (1u << p.key_bits) - 1u;
+    unsigned set = 0;
+    if (oa.type == PG_HASH_FSUM || oa.type == PG_HASH_PSUM) {
+        const int nd = oa.type == PG_HASH_PSUM ? 2 : p.n;
+        unsigned sum = 0;
+        int movable = 0, others = 0;
+        for (int i = 0; i < p.n; i++) {
+            const unsigned pc = key.field(i * p.key_bits, fmask);
+            if (i < nd) {
+                sum += pc;
+                movable += (int)pc < p.len[i];
+            } else {
+                others += (int)pc < p.len[i];
+            }
+        }
+        for (int k = others ? 0 : 1; k <= movable; k++) set |= 1u << (((sum + k) >> oa.shift) % (unsigned)n_parts);
+    } else {
+        unsigned wbase = 0, delta[8];
+        for (int k = 0; k < oa.nfc; k++) {
+            const int co = oa.fc[k];
+            const unsigned pc = key.field(co * p.key_bits, fmask);
+            unsigned dl = 0;
+            for (int m = 0; m < oa.nb; m++) {
+                if (!((oa.fcm[k] >> m) & 1)) continue;
+                const unsigned v0 = (pc >> oa.bit[m]) & 1u, v1 = ((pc + 1u) >> oa.bit[m]) & 1u;
+                wbase |= v0 << m;
+                dl |= (v0 ^ v1) << m;
+            }
+            delta[k] = (int)pc < p.len[co] ? dl : 0u; // a sequence at its end does not move (borderCheck, Node.cpp:69-77)
+        }
+        for (int sset = 0; sset < (1 << oa.nfc); sset++) {
+            unsigned w = wbase;
+            bool real = true;
+            for (int k = 0; k < oa.nfc; k++)
+                if ((sset >> k) & 1) {
+                    w ^= delta[k];
+                    real = real && delta[k] != 0; // moving a coordinate that changes nothing is the same class
+                }
+            if (real) set |= 1u << (w % (unsigned)n_parts);
+        }
+    }
+    return set & ~(1u << part);
+}
 
 constexpr unsigned long long HINT_FLAG = 1ull << 31; // record word KEYW+1: {start slot : 32 | HINT_FLAG | move mask : 16}
 constexpr int RING_CAP = 64;                         // survivor ring, items per warp
 constexpr int PLAN_SM = 2048;
 
-template <int KEYW>
-__global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevSearch d)
+template <int KEYW, bool FWD>
+__global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
+                                                    const __grid_constant__ OwnerArgs oa)
 {
     __shared__ uint32_t s_plan[PLAN_SM];
     SearchCtrl *c = d.ctrl;
@@ -666,14 +733,43 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
             }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, live);
-        int wbase = 0;
-        if (lane == 0 && bal) wbase = atomicAdd(&c->live_n, __popc(bal));
+        unsigned long long wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&c->live_n, (unsigned long long)__popc(bal));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
         if (live) {
             unsigned long long *r = d.live + (size_t)(wbase + __popc(bal & lt));
             r[0] = klo;
             if constexpr (KEYW == 2) r[d.live_cap] = khi;
             r[KEYW * d.live_cap] = val;
+        }
+        if constexpr (FWD) {
+            // Parent forwarding: every partition that owns a successor of this node gets the node itself (16 or 24
+            // bytes over NVLink) and generates its own successors from it, instead of receiving them one by one.
+            unsigned owners = 0;
+            if (live) {
+                Key<KEYW> key;
+                key.lo = klo;
+                if constexpr (KEYW == 2) key.hi = khi;
+                owners = successor_owners<KEYW>(p, oa, key, d.n_parts, d.part);
+            }
+            for (int dst = 0; dst < d.n_parts; dst++) {
+                const unsigned b = __ballot_sync(0xffffffffu, (owners >> dst) & 1u);
+                if (!b) continue;
+                unsigned long long base0 = 0;
+                if (lane == __ffs(b) - 1) base0 = atomicAdd(&d.outbox_count[dst], (unsigned long long)__popc(b));
+                base0 = __shfl_sync(0xffffffffu, base0, __ffs(b) - 1);
+                if ((owners >> dst) & 1u) {
+                    const unsigned long long i = base0 + __popc(b & lt);
+                    if (i < d.outbox_cap) {
+                        unsigned long long *r = reinterpret_cast<unsigned long long *>(d.peer_inbox[dst]) + (size_t)d.part * d.outbox_cap * (KEYW + 1) + i;
+                        r[0] = klo;
+                        if constexpr (KEYW == 2) r[d.outbox_cap] = khi;
+                        r[KEYW * d.outbox_cap] = val;
+                    } else {
+                        c->error = 4;
+                    }
+                }
+            }
         }
     }
 }
@@ -738,10 +834,14 @@ __device__ __forceinline__ void ring_flush(const DevSearch &d, const unsigned lo
     for (unsigned w = lane; w < count * XW; w += 32) dst[w] = src[w];
 }
 
-template <int N, int KEYW, bool MULTI>
+// MODE 0: one partition.  MODE 1: successors owned by other partitions are sent to them as records.  MODE 2: they are
+// skipped - their owners generate them from the forwarded parent (claim_kernel<.., true>).
+template <int N, int KEYW, int MODE>
 __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
-                                                              const __grid_constant__ OwnerArgs oa)
+                                                              const __grid_constant__ OwnerArgs oa, const __grid_constant__ ParentSrc ps)
 {
+    constexpr bool MULTI = MODE != 0;   // owners are computed
+    constexpr bool SEND = MODE == 1;    // ... and records sent
     using C = ExpCfg<N>;
     constexpr int XW = KEYW == 1 ? 3 : 4;
     constexpr int GROUPS = 256 / C::LP;
@@ -755,11 +855,16 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
     unsigned long long *s_ring = reinterpret_cast<unsigned long long *>(s_keyhigh + C::H); // [8 warps][RING_CAP][XW]
     int *s_groups = reinterpret_cast<int *>(s_ring + 8 * RING_CAP * XW);
     __shared__ unsigned long long s_cnt[4];
-    __shared__ unsigned long long s_obox[MULTI ? 64 : 1];
+    __shared__ unsigned long long s_obox[SEND ? 64 : 1];
+    __shared__ unsigned char s_mod[MULTI ? 256 : 1]; // owner word -> partition
 
     SearchCtrl *c = d.ctrl;
-    const int live_n = (c->done || c->error) ? 0 : c->live_n;
-    if (live_n == 0) return;
+    if (c->done || c->error) return;
+    {
+        unsigned long long any = 0;
+        for (int rg = 0; rg < ps.n; rg++) any |= *ps.count[rg];
+        if (any == 0) return;
+    }
     const int limit = min(c->prune_limit, c->best_goal);
 
     pg_load_pair_meta(p, meta);
@@ -770,7 +875,8 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
         s_keyhigh[hi] = k;
     }
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-    if (MULTI && threadIdx.x < 64) s_obox[threadIdx.x] = (unsigned long long)OBOX_CHUNK; // no chunk yet: the first append opens one
+    if (SEND && threadIdx.x < 64) s_obox[threadIdx.x] = (unsigned long long)OBOX_CHUNK; // no chunk yet: the first append opens one
+    if (MULTI) s_mod[threadIdx.x & 255] = (unsigned char)((threadIdx.x & 255) % (unsigned)d.n_parts);
     __syncthreads();
 
     const int grp = threadIdx.x / C::LP, sub = threadIdx.x % C::LP;
@@ -792,13 +898,16 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
 
     // parents are dealt to the groups round-robin; the trip count is warp-uniform (the ring is a warp-level structure)
     const int stride = gridDim.x * GROUPS;
+    for (int rg = 0; rg < ps.n; rg++) {
+    const unsigned long long *live = ps.base[rg];
+    const int live_n = (int)min(*ps.count[rg], ps.cap);
     int pi = blockIdx.x * GROUPS + grp;
     unsigned long long nk0 = 0, nk1 = 0, nval = 0;
     if (pi < live_n) {
-        const unsigned long long *r = d.live + (size_t)pi;
+        const unsigned long long *r = live + (size_t)pi;
         nk0 = __ldg(r);
-        if constexpr (KEYW == 2) nk1 = __ldg(r + d.live_cap);
-        nval = __ldg(r + KEYW * d.live_cap);
+        if constexpr (KEYW == 2) nk1 = __ldg(r + ps.cap);
+        nval = __ldg(r + KEYW * ps.cap);
     }
     for (int wfirst = blockIdx.x * GROUPS + warp * GPW; wfirst < live_n; wfirst += stride, pi += stride) {
         bool act = pi < live_n;
@@ -807,10 +916,10 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
         if constexpr (KEYW == 2) pkey.hi = nk1;
         const unsigned long long val = nval;
         if (pi + stride < live_n) { // the next parent's record travels while this one is expanded
-            const unsigned long long *r = d.live + (size_t)(pi + stride);
+            const unsigned long long *r = live + (size_t)(pi + stride);
             nk0 = __ldg(r);
-            if constexpr (KEYW == 2) nk1 = __ldg(r + d.live_cap);
-            nval = __ldg(r + KEYW * d.live_cap);
+            if constexpr (KEYW == 2) nk1 = __ldg(r + ps.cap);
+            nval = __ldg(r + KEYW * ps.cap);
         }
         int pos[N];
         int goal_mask = 0;
@@ -830,8 +939,30 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
             } else {
                 // the goal is reached from here by moving every sequence that is one short of its end
                 goal_mask = alive == onestep ? alive : 0;
-                if (sub == 0) n_exp++;
+                if (sub == 0 && ps.own) n_exp++;
                 pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
+            }
+        }
+        unsigned wbase = 0;
+        unsigned wflip[C::HB > 0 ? C::HB : 1];
+#pragma unroll
+        for (int b = 0; b < C::HB; b++) wflip[b] = 0;
+        if constexpr (MULTI) {
+            if (oa.type != PG_HASH_FSUM && oa.type != PG_HASH_PSUM) {
+                for (int m = 0; m < oa.nb; m++) {
+                    const int co = oa.co[m];
+                    if (co < 0) continue;
+                    const unsigned pc = pkey.field(co * p.key_bits, fmask);
+                    const unsigned v0 = (pc >> oa.bit[m]) & 1u, v1 = ((pc + 1u) >> oa.bit[m]) & 1u;
+                    if (co < C::A) {
+                        wbase |= (((sub >> co) & 1) ? v1 : v0) << m;
+                    } else {
+                        wbase |= v0 << m;
+#pragma unroll
+                        for (int b = 0; b < C::HB; b++)
+                            if (co - C::A == b) wflip[b] |= (v0 ^ v1) << m;
+                    }
+                }
             }
         }
         PH_MARK(2); // prepare (LUT gathers, HH, B/E)
@@ -863,6 +994,27 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
                     lk[j] = lv[j] = 0;
                     ls[j] = 0;
                     lg[j] = 0;
+                    int own = d.part;
+                    if constexpr (MULTI) {
+                        if (v) {
+                            if (oa.type == PG_HASH_FSUM || oa.type == PG_HASH_PSUM) {
+                                const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                                unsigned sm = 0;
+                                const int nd = oa.type == PG_HASH_PSUM ? 2 : N;
+                                for (int q = 0; q < nd; q++) sm += key.field(q * p.key_bits, fmask);
+                                own = (int)((sm >> oa.shift) % (unsigned)d.n_parts);
+                            } else {
+                                // the owner word of a successor differs from wbase (this lane, no high move) only in the
+                                // bits tied to the high coordinates that move: one XOR per moved coordinate
+                                unsigned w = wbase;
+#pragma unroll
+                                for (int b = 0; b < C::HB; b++)
+                                    if ((high >> b) & 1) w ^= wflip[b];
+                                own = (int)s_mod[w];
+                            }
+                            if (MODE == 2 && own != d.part) v = false; // its owner generates it from the forwarded parent
+                        }
+                    }
                     if (v) {
                         const int gn = vg[i] + s_hhg[high];
                         const int f = gn + vh[i] + s_hhh[high];
@@ -877,23 +1029,10 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
                     }
                     if (v) {
                         const Key<KEYW> key = klow.plus(s_keyhigh[high]);
-                        if constexpr (MULTI) {
-                            unsigned own;
-                            if (oa.type == PG_HASH_FSUM || oa.type == PG_HASH_PSUM) {
-                                unsigned s = 0;
-                                const int nd = oa.type == PG_HASH_PSUM ? 2 : N;
-                                for (int q = 0; q < nd; q++) s += key.field(q * p.key_bits, fmask);
-                                own = (s >> oa.shift) % (unsigned)d.n_parts;
-                            } else {
-                                unsigned w = 0;
-#pragma unroll
-                                for (int m = 0; m < 8; m++)
-                                    if (m < oa.nb && oa.sh[m] >= 0) w |= key.field(oa.sh[m], 1u) << m;
-                                own = w % (unsigned)d.n_parts;
-                            }
-                            if ((int)own != d.part) { // remote successor: goes to the owner's outbox below
+                        if constexpr (SEND) {
+                            if (own != d.part) { // remote successor: goes to the owner's outbox below
                                 rem = true;
-                                rown = (int)own;
+                                rown = own;
                                 v = false;
                             }
                         }
@@ -906,7 +1045,7 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
                             vmask |= 1u << j;
                         }
                     }
-                    if constexpr (MULTI) { // one reservation per (warp, destination) from the CTA's outbox chunks
+                    if constexpr (SEND) { // one reservation per (warp, destination) from the CTA's outbox chunks
                         unsigned todo = __ballot_sync(0xffffffffu, rem);
                         while (todo) {
                             const int leader = __ffs(todo) - 1;
@@ -981,6 +1120,7 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
         }
         __syncwarp(); // the group's LUTs are rewritten by the next parent
     }
+    } // parent regions
     if (qtail != qhead) ring_flush<XW>(d, wq, qhead, qtail - qhead, lane);
     PH_MARK(5);
 #ifdef PG_PHASE_TIMING
@@ -989,7 +1129,7 @@ __global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_const
 #endif
 
     // ---- close the CTA's open outbox chunks
-    if constexpr (MULTI) {
+    if constexpr (SEND) {
         __syncthreads();
         if ((int)threadIdx.x < d.n_parts) {
             const unsigned long long st = s_obox[threadIdx.x];
@@ -1395,7 +1535,7 @@ DevSearch dev_search(const pg_ctx *ctx)
     d.outbox_cap = s->outbox_cap;
     d.p2p = s->p2p ? 1 : 0;
     // P2P mode: this round's half of the double-buffered inboxes / count arrays
-    const size_t half = (size_t)s->cfg.n_parts * s->outbox_cap * s->xrec;
+    const size_t half = (size_t)s->cfg.n_parts * s->region_bytes;
     for (int i = 0; i < 16; i++) {
         d.peer_inbox[i] = s->peer_inbox[i] ? (char *)s->peer_inbox[i] + (size_t)s->p2p_buf * half : nullptr;
         d.peer_counts[i] = s->peer_counts[i] ? s->peer_counts[i] + (size_t)s->p2p_buf * s->cfg.n_parts : nullptr;
@@ -1407,8 +1547,35 @@ DevSearch dev_search(const pg_ctx *ctx)
     return d;
 }
 
-template <int N, int KEYW, bool MULTI>
-int launch_expand_round(pg_ctx *ctx, cudaStream_t st)
+OwnerArgs owner_args(const pg_ctx *ctx)
+{
+    const SearchState *s = ctx->search;
+    OwnerArgs oa;
+    memset(&oa, 0, sizeof(oa));
+    oa.type = ctx->dp.hash_type;
+    oa.shift = ctx->dp.hash_shift;
+    const int nd = ctx->dp.hash_type == PG_HASH_PZORDER ? 2 : ctx->n;
+    oa.nb = std::min(8, ilog2i(std::max(1, s->cfg.n_parts)) + 2);
+    for (int m = 0; m < 8; m++) {
+        const int q = ctx->dp.hash_shift + m;
+        const int coord = q % nd, bit = q / nd;
+        oa.co[m] = bit < ctx->dp.key_bits ? coord : -1;
+        oa.bit[m] = bit;
+    }
+    for (int m = 0; m < oa.nb; m++) { // group the owner-word bits by the coordinate they read
+        if (oa.co[m] < 0) continue;
+        int k = 0;
+        while (k < oa.nfc && oa.fc[k] != oa.co[m]) k++;
+        if (k == oa.nfc) oa.fc[oa.nfc++] = oa.co[m];
+        oa.fcm[k] |= 1 << m;
+    }
+    return oa;
+}
+
+// MODE as in expand_probe_kernel; inbox = false: this partition's own live parents, true: the parents forwarded by the
+// other partitions (MODE 2)
+template <int N, int KEYW, int MODE>
+int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
 {
     using C = ExpCfg<N>;
     SearchState *s = ctx->search;
@@ -1418,37 +1585,49 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st)
                         sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
     static int occ = 0;
     if (!occ) {
-        PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, MULTI>, 256, smem));
+        PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, MODE>, 256, smem));
         if (occ < 1) occ = 1;
     }
     // persistent grid: resident CTAs per SM x SM count, capped by the parent groups of a full batch
     long long grid = (long long)ctx->sm_count * occ;
     const long long want = (s->batch_target + GROUPS - 1) / GROUPS;
     if (grid > want) grid = std::max<long long>(1, want);
-    OwnerArgs oa;
-    oa.type = ctx->dp.hash_type;
-    oa.shift = ctx->dp.hash_shift;
-    const int nd = ctx->dp.hash_type == PG_HASH_PZORDER ? 2 : ctx->n;
-    for (int m = 0; m < 8; m++) {
-        const int q = ctx->dp.hash_shift + m;
-        const int coord = q % nd, bit = q / nd;
-        oa.sh[m] = bit < ctx->dp.key_bits ? coord * ctx->dp.key_bits + bit : -1;
+    const DevSearch d = dev_search(ctx);
+    ParentSrc ps;
+    memset(&ps, 0, sizeof(ps));
+    if (!inbox) {
+        ps.n = 1;
+        ps.own = 1;
+        ps.cap = s->live_cap;
+        ps.base[0] = s->d_live;
+        ps.count[0] = &s->d_ctrl->live_n;
+    } else {
+        ps.own = 0;
+        ps.cap = s->outbox_cap;
+        for (int src = 0; src < s->cfg.n_parts; src++) {
+            if (src == s->cfg.part) continue;
+            ps.base[ps.n] = reinterpret_cast<const unsigned long long *>(d.peer_inbox[s->cfg.part]) + (size_t)src * s->outbox_cap * (KEYW + 1);
+            ps.count[ps.n] = d.peer_counts[s->cfg.part] + src;
+            ps.n++;
+        }
     }
-    oa.nb = std::min(8, ilog2i(std::max(1, s->cfg.n_parts)) + 2);
-    expand_probe_kernel<N, KEYW, MULTI><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, dev_search(ctx), oa);
+    expand_probe_kernel<N, KEYW, MODE><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, d, owner_args(ctx), ps);
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
 }
 
 template <int KEYW>
-int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st)
+int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st, bool inbox = false)
 {
-    const bool multi = ctx->search->cfg.n_parts > 1;
+    const SearchState *s = ctx->search;
+    const int mode = s->cfg.n_parts == 1 ? 0 : (s->forward ? 2 : 1);
     switch (ctx->n) {
-#define CASE(X) \
-    case X:     \
-        return multi ? launch_expand_round<X, KEYW, true>(ctx, st) : launch_expand_round<X, KEYW, false>(ctx, st);
+#define CASE(X)                                                                    \
+    case X:                                                                        \
+        if (mode == 0) return launch_expand_round<X, KEYW, 0>(ctx, st, inbox);     \
+        if (mode == 1) return launch_expand_round<X, KEYW, 1>(ctx, st, inbox);     \
+        return launch_expand_round<X, KEYW, 2>(ctx, st, inbox);
         CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(14) CASE(16)
 #undef CASE
     }
@@ -1481,6 +1660,24 @@ int prof_harvest(pg_ctx *ctx) // after a stream synchronise
         s->insert_ms += t[3];
     }
     s->prof_used = 0;
+    for (size_t i = 0; i + 2 <= s->prof_used2; i += 2) {
+        float t = 0;
+        PG_CUDA(ctx, cudaEventElapsedTime(&t, s->prof_ev2[i], s->prof_ev2[i + 1]));
+        s->inbox_ms += t;
+    }
+    s->prof_used2 = 0;
+    return PG_OK;
+}
+
+int prof_event2(pg_ctx *ctx)
+{
+    SearchState *s = ctx->search;
+    if (s->prof_used2 == s->prof_ev2.size()) {
+        cudaEvent_t e;
+        PG_CUDA(ctx, cudaEventCreate(&e));
+        s->prof_ev2.push_back(e);
+    }
+    PG_CUDA(ctx, cudaEventRecord(s->prof_ev2[s->prof_used2++], ctx->stream));
     return PG_OK;
 }
 
@@ -1518,19 +1715,34 @@ int launch_round(pg_ctx *ctx, int f_limit)
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     {
         const long long grid = std::min<long long>((s->batch_target + 255) / 256, (long long)ctx->sm_count * 8);
-        if (s->keyw == 1)
-            claim_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx));
-        else
-            claim_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx));
+        const DevSearch d = dev_search(ctx);
+        const OwnerArgs oa = owner_args(ctx);
+        if (s->forward) {
+            if (s->keyw == 1)
+                claim_kernel<1, true><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+            else
+                claim_kernel<2, true><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+        } else {
+            if (s->keyw == 1)
+                claim_kernel<1, false><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+            else
+                claim_kernel<2, false><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+        }
         PG_CUDA(ctx, cudaGetLastError());
+        if (s->forward) { // the forwarded parents' counts follow them at once: the owners' barrier is the next thing on every stream
+            publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(d);
+            PG_CUDA(ctx, cudaGetLastError());
+        }
     }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
     if (rc != PG_OK) return rc;
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
-    if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
+    if (!s->forward) { // forwarding: the survivors are inserted after the forwarded parents have been expanded as well
+        if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
+    }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
-    if (s->p2p && s->peer_counts[0]) {
+    if (!s->forward && s->p2p && s->peer_counts[0]) {
         publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx));
         PG_CUDA(ctx, cudaGetLastError());
     }
@@ -1576,6 +1788,7 @@ void fill_counters(const SearchState *s, pg_result *r)
     r->expand_ms = s->expand_ms;
     r->select_ms = s->select_ms;
     r->survivors = (int64_t)c->table_used;
+    r->inbox_ms = s->inbox_ms;
     r->claim_ms = s->claim_ms;
     r->insert_ms = s->insert_ms;
 #ifdef PG_PHASE_TIMING
@@ -1608,6 +1821,7 @@ void pg_search_free(pg_ctx *ctx)
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->prof_ev2) cudaEventDestroy(e);
     delete s;
     ctx->search = nullptr;
 }
@@ -1711,11 +1925,23 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
         PG_CUDA(ctx, cudaMalloc(&s->d_host_counts, 8 * 64));
     }
     if (cfg->n_parts > 1) {
-        // worst case every successor of a full batch goes to one destination
-        const uint64_t S = (1ull << ctx->n) - 1;
-        s->outbox_cap = (uint64_t)(s->batch_target + UNIT) * S + (uint64_t)OBOX_CHUNK * 8 * (uint64_t)ctx->sm_count;
-        if (cfg->reserved != 1) // reserved == 1: P2P mode, records go straight to the peers' inboxes (pg_search_set_peers)
-            PG_CUDA(ctx, cudaMalloc(&s->d_outbox, (size_t)cfg->n_parts * s->outbox_cap * s->xrec));
+        s->forward = cfg->reserved == 2;
+        if (s->forward) {
+            // parent forwarding: a destination receives at most every live parent of the round
+            s->outbox_cap = (uint64_t)s->batch_target + UNIT;
+            s->region_bytes = (size_t)s->outbox_cap * (s->keyw + 1) * 8;
+        } else {
+            // worst case every successor of a full batch goes to one destination
+            const uint64_t S = (1ull << ctx->n) - 1;
+            s->outbox_cap = (uint64_t)(s->batch_target + UNIT) * S;
+            // beyond four partitions the worst case is sized at 4x the share a uniform hash gives one destination; a round
+            // that needs more ends the run with PG_ERR_CAPACITY ("outbox overflow") instead of writing out of bounds
+            if (cfg->n_parts > 4) s->outbox_cap = s->outbox_cap * 4 / cfg->n_parts;
+            s->outbox_cap += (uint64_t)OBOX_CHUNK * 8 * (uint64_t)ctx->sm_count;
+            s->region_bytes = (size_t)s->outbox_cap * s->xrec;
+            if (cfg->reserved != 1) // reserved == 1: P2P mode, records go straight to the peers' inboxes (pg_search_set_peers)
+                PG_CUDA(ctx, cudaMalloc(&s->d_outbox, (size_t)cfg->n_parts * s->outbox_cap * s->xrec));
+        }
         PG_CUDA(ctx, cudaMalloc(&s->d_outbox_count, 8 * 64));
         PG_CUDA(ctx, cudaMallocHost(&s->h_outbox_count, 8 * 64));
         PG_CUDA(ctx, cudaMemsetAsync(s->d_outbox_count, 0, 8 * 64, ctx->stream));
@@ -1750,7 +1976,7 @@ extern "C" int pg_search_round(pg_ctx *ctx, int32_t f_limit)
     if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     SearchState *s = ctx->search;
-    if (s->cfg.n_parts > 1 && s->cfg.reserved == 1 && !s->p2p) return pg_fail(ctx, PG_ERR_STATE, "P2P mode requested but pg_search_set_peers has not run");
+    if (s->cfg.n_parts > 1 && s->cfg.reserved >= 1 && !s->p2p) return pg_fail(ctx, PG_ERR_STATE, "P2P mode requested but pg_search_set_peers has not run");
     int rc = launch_round(ctx, f_limit);
     if (rc != PG_OK) return rc;
     if (s->cfg.n_parts > 1)
@@ -1763,7 +1989,7 @@ extern "C" int pg_search_round_async(pg_ctx *ctx, int32_t f_limit)
     if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     SearchState *s = ctx->search;
-    if (s->cfg.n_parts > 1 && s->cfg.reserved == 1 && !s->p2p) return pg_fail(ctx, PG_ERR_STATE, "P2P mode requested but pg_search_set_peers has not run");
+    if (s->cfg.n_parts > 1 && s->cfg.reserved >= 1 && !s->p2p) return pg_fail(ctx, PG_ERR_STATE, "P2P mode requested but pg_search_set_peers has not run");
     return launch_round(ctx, f_limit);
 }
 
@@ -1820,15 +2046,30 @@ extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
     SearchState *s = ctx->search;
     if (!s->p2p || !s->peer_counts[s->cfg.part]) return pg_fail(ctx, PG_ERR_STATE, "pg_search_insert_inbox_async needs pg_search_set_peers and pg_search_set_peer_counts");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
-    const DevSearch d = dev_search(ctx);
-    const size_t region = (size_t)s->outbox_cap * s->xrec;
-    for (int src = 0; src < s->cfg.n_parts; src++) {
-        if (src == s->cfg.part) continue;
-        int rc = launch_insert(ctx, d.peer_inbox[s->cfg.part] + (size_t)src * region, d.peer_counts[s->cfg.part] + src, s->outbox_cap);
+    int rc;
+    if (s->profile && (rc = prof_event2(ctx)) != PG_OK) return rc;
+    if (s->forward) {
+        // expand the parents the other partitions forwarded (only the successors this partition owns), then insert
+        // the round's survivors: those of its own parents and of the forwarded ones
+        rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream, true) : launch_expand_round_k<2>(ctx, ctx->stream, true);
         if (rc != PG_OK) return rc;
+        if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
+    } else {
+        const DevSearch d = dev_search(ctx);
+        for (int src = 0; src < s->cfg.n_parts; src++) {
+            if (src == s->cfg.part) continue;
+            rc = launch_insert(ctx, d.peer_inbox[s->cfg.part] + (size_t)src * s->region_bytes, d.peer_counts[s->cfg.part] + src, s->outbox_cap);
+            if (rc != PG_OK) return rc;
+        }
     }
+    if (s->profile && (rc = prof_event2(ctx)) != PG_OK) return rc;
     s->p2p_buf = (s->p2p_buf + 1) % s->p2p_nbuf;
     return PG_OK;
+}
+
+extern "C" int64_t pg_search_region_bytes(const pg_ctx *ctx)
+{
+    return ctx && ctx->search ? (int64_t)ctx->search->region_bytes : 0;
 }
 
 extern "C" int64_t pg_search_outbox_capacity(const pg_ctx *ctx)

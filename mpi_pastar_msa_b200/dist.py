@@ -70,26 +70,36 @@ class CudaEngine:
 
 
 class CudaEngineP2P(CudaEngine):
-    """Fused expansion + exchange: the expand kernel stores remote successors straight into the owner's inbox over
-    NVLink (peer-mapped symmetric memory); only the per-destination counts travel by collective.  Replaces the
-    bulk all-to-all of CudaEngine (same records, same insert kernel)."""
+    """Fused expansion + exchange, device-driven: the expand kernel stores remote successors straight into the owner's
+    inbox over NVLink (peer-mapped symmetric memory) while it computes, a one-thread-per-destination kernel stores the
+    record counts next to them, one cross-GPU barrier runs on the stream (symmetric-memory signal pads), and the insert
+    kernels read their counts from device memory.  No collective and no host round trip per round; inboxes and count
+    arrays are double-buffered so one barrier per round is enough.  Same records and insert kernel as CudaEngine."""
 
-    def __init__(self, gpu, n_parts, part, dist, table_capacity=0, batch_target=0):
+    async_rounds = True
+
+    def __init__(self, gpu, n_parts, part, dist, table_capacity=0, batch_target=0, forward=True):
         import torch
         import torch.distributed._symmetric_memory as symm
+        self.forward = forward
         self.torch, self.g, self.n_parts, self.part = torch, gpu, n_parts, part
         if n_parts > 16:
             raise ValueError("P2P mode supports up to 16 partitions")
         self.device = torch.device("cuda", torch.cuda.current_device())
         gpu.set_stream(torch.cuda.current_stream().cuda_stream)
-        gpu.search_begin(n_parts, part, table_capacity, batch_target, p2p=True)
-        self.xrec = gpu.xrec_stride()
-        self.region = gpu.search_outbox_capacity() * self.xrec          # bytes one source may write into one inbox
-        self.inbox = symm.empty(n_parts * self.region, dtype=torch.uint8, device=self.device)
+        gpu.search_begin(n_parts, part, table_capacity, batch_target, p2p=2 if forward else 1)
+        self.xrec = gpu.xrec_stride() if not forward else 8 * (2 if gpu.xrec_stride() == 24 else 3)
+        self.region = gpu.search_region_bytes()                        # bytes one source may write into one inbox
+        self.inbox = symm.empty(2 * n_parts * self.region, dtype=torch.uint8, device=self.device)
         self.hdl = symm.rendezvous(self.inbox, dist.group.WORLD)
+        self.counts = symm.empty(2 * n_parts, dtype=torch.int64, device=self.device)
+        self.counts.zero_()
+        self.hdl_c = symm.rendezvous(self.counts, dist.group.WORLD)
         gpu.search_set_peers([int(self.hdl.buffer_ptrs[r]) for r in range(n_parts)])
-        self.counts = self._wrap64(gpu.search_outbox_counts_dev(), n_parts)
-        self.bytes_sent = 0
+        gpu.search_set_peer_counts([int(self.hdl_c.buffer_ptrs[r]) for r in range(n_parts)], 2)
+        self.sent = self._wrap64(gpu.search_outbox_counts_dev(), n_parts)   # this round's records per destination
+        self.sent_total = torch.zeros(1, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize()
         dist.barrier()
 
     def _wrap64(self, ptr, n):
@@ -97,16 +107,19 @@ class CudaEngineP2P(CudaEngine):
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
         return self.torch.as_tensor(_Mem(), device=self.device)
 
+    @property
+    def bytes_sent(self):
+        return int(self.sent_total.item()) * self.xrec
+
     def round_and_exchange(self, f_limit, dist):
-        t = self.torch
-        self.g.search_round(f_limit)                       # remote successors are already in their owners' inboxes
-        allc = t.empty(self.n_parts * self.n_parts, dtype=t.int64, device=self.device)
-        dist.all_gather_into_tensor(allc, self.counts)     # also orders every rank's stores before any insert
-        allc = allc.view(self.n_parts, self.n_parts)
-        mine = allc[:, self.part].tolist()                 # records source s wrote into my region s
-        mine[self.part] = 0
-        self.bytes_sent += int(allc[self.part].sum().item()) * self.xrec
-        self.g.search_insert_segments_dev(self.inbox.data_ptr(), self.region, mine)
+        self.g.search_round_async(f_limit)     # remote successors + their counts are on their way to the owners
+        self.sent_total += self.sent.sum()     # bookkeeping only (device side)
+        self.hdl.barrier(channel=0)            # every partition's stores of this round are complete and visible
+        self.g.search_insert_inbox_async()     # dedupe + push what the other partitions sent; flips the buffers
+
+    def status(self):
+        self.g.search_sync()
+        return self.g.search_status()
 
 
 class PartitionedSearch:
@@ -121,6 +134,7 @@ class PartitionedSearch:
         self.max_expansions = max_expansions
         self.rounds = 0
         self.bytes_sent = 0
+        self.rounds_per_status = 4
 
     def _dev(self):
         return getattr(self.e, "device", self.torch.device("cpu"))
@@ -141,15 +155,18 @@ class PartitionedSearch:
         self.bytes_sent += int(sum(send_l))
         return inbox
 
-    def step(self, f_limit=INT_MAX):
-        """One round; returns (global min open f, global best goal g, global expansions)."""
+    def step(self, f_limit=INT_MAX, rounds=1):
+        """`rounds` rounds, then one status exchange; returns (global min open f, global best goal g, global counters)."""
         t, dist = self.torch, self.dist
+        for _ in range(rounds):
+            if hasattr(self.e, "round_and_exchange"):
+                self.e.round_and_exchange(f_limit, dist)
+            else:
+                outboxes = self.e.round(f_limit)
+                self.e.insert(self.exchange(outboxes))
+            self.rounds += 1
         if hasattr(self.e, "round_and_exchange"):
-            self.e.round_and_exchange(f_limit, dist)
             self.bytes_sent = self.e.bytes_sent
-        else:
-            outboxes = self.e.round(f_limit)
-            self.e.insert(self.exchange(outboxes))
         mn, best, cnt = self.e.status()
         # one small collective for the stop test and the counters: min over ranks of {min open f, best goal g}
         # (PAStar.cpp:502-519) and the sums
@@ -159,14 +176,16 @@ class PartitionedSearch:
         allv = allv.view(self.world, 5)
         mins = allv[:, :2].min(dim=0).values.tolist()
         tot = allv[:, 2:].sum(dim=0).tolist()
-        self.rounds += 1
         return int(mins[0]), int(mins[1]), [int(x) for x in tot]
 
     def run(self):
         """Search to the optimality-preserving stop (or the expansion budget).  Returns a dict on every rank."""
         best = INT_MAX
+        # device-driven engines chain a few rounds between status exchanges: rounds past the optimum only pop nodes
+        # with f >= g* on partitions that have not heard of the goal yet, which cannot change the result
+        per = self.rounds_per_status if getattr(self.e, "async_rounds", False) else 1
         while True:
-            mn, best, tot = self.step(best)
+            mn, best, tot = self.step(best, per)
             if mn >= best or mn == INT_MAX:  # every open node everywhere has f >= g_goal; nothing in flight
                 finished = best != INT_MAX
                 break

@@ -6,6 +6,7 @@ import numpy as np, torch, torch.distributed as dist
 import mpi_pastar_msa_b200 as m
 from mpi_pastar_msa_b200.dist import CudaEngine, CudaEngineP2P, PartitionedSearch
 P2P = os.environ.get('PG_P2P', '1') == '1'
+FWD = os.environ.get('PG_FWD', '1') == '1'
 from conftest import CASES, KNOWN_OPT, weighted_sp_score
 from oracle import oracle as O
 
@@ -19,7 +20,7 @@ for name, batch, ht, sh in [("PF08184", 64, "FZORDER", 3), ("test2", 256, "FSUM"
     G = m.PastarGPU(seqs, device=local)
     G.build_pair_tables()
     G.configure_hash(ht, sh)
-    eng = CudaEngineP2P(G, world, rank, dist, 1 << 26, batch) if P2P else CudaEngine(G, world, rank, 1 << 26, batch)
+    eng = CudaEngineP2P(G, world, rank, dist, 1 << 26, batch, forward=FWD) if P2P else CudaEngine(G, world, rank, 1 << 26, batch)
     drv = PartitionedSearch(eng, dist, seqs, lambda pos: int(G.owner(np.array(pos, dtype=np.uint16), world)[0]))
     torch.cuda.synchronize(); t0 = time.time()
     r = drv.run()
