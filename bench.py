@@ -200,7 +200,7 @@ def run_ours(args, rank, world):
         G.search_end()
     else:
         from mpi_pastar_msa_b200.dist import CudaEngine, CudaEngineP2P, PartitionedSearch
-        G.configure_hash("FZORDER", 12)
+        G.configure_hash("FZORDER", args.hash_shift)
         try:  # fused expansion + exchange over peer-mapped inboxes; NCCL all-to-all if symmetric memory is unavailable
             if os.environ.get("PG_P2P", "1") == "0":
                 raise RuntimeError("PG_P2P=0")
@@ -260,7 +260,7 @@ def run_ours(args, rank, world):
     clocks = sampler.result()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "table_slots_per_gpu": cap, "parallelism": "hash-partition x%d" % world,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "table_slots_per_gpu": cap, "parallelism": "hash-partition x%d" % world + ("" if world == 1 else " (FZORDER shift %d)" % args.hash_shift),
                        "ramp_up_rounds_untimed": ramp,
                        "l2": "inputs larger than L2: %.1f GiB hash table per GPU, ~%d MB of distinct sectors touched per step"
                              % (cap * 16 / 2**30, batch * 127 * 32 // 10**6)},
@@ -379,6 +379,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="open-list entries popped per round and GPU")
     ap.add_argument("--table-capacity", type=int, default=1 << 30)
+    ap.add_argument("--hash-shift", type=int, default=17,
+                    help="FZORDER owner-hash shift for N > 1 (the reference's -s, 0..21; its default 12 puts owner bits at bit 1 of two coordinates, 17 at bit 2 of three: fewer parents straddle partitions)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

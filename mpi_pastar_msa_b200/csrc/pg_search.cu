@@ -687,9 +687,8 @@ constexpr unsigned long long HINT_FLAG = 1ull << 31; // record word KEYW+1: {sta
 constexpr int RING_CAP = 64;                         // survivor ring, items per warp
 constexpr int PLAN_SM = 2048;
 
-template <int KEYW, bool FWD>
-__global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
-                                                    const __grid_constant__ OwnerArgs oa)
+template <int KEYW>
+__global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevSearch d)
 {
     __shared__ uint32_t s_plan[PLAN_SM];
     SearchCtrl *c = d.ctrl;
@@ -742,32 +741,49 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevP
             if constexpr (KEYW == 2) r[d.live_cap] = khi;
             r[KEYW * d.live_cap] = val;
         }
-        if constexpr (FWD) {
-            // Parent forwarding: every partition that owns a successor of this node gets the node itself (16 or 24
-            // bytes over NVLink) and generates its own successors from it, instead of receiving them one by one.
-            unsigned owners = 0;
-            if (live) {
-                Key<KEYW> key;
-                key.lo = klo;
-                if constexpr (KEYW == 2) key.hi = khi;
-                owners = successor_owners<KEYW>(p, oa, key, d.n_parts, d.part);
-            }
-            for (int dst = 0; dst < d.n_parts; dst++) {
-                const unsigned b = __ballot_sync(0xffffffffu, (owners >> dst) & 1u);
-                if (!b) continue;
-                unsigned long long base0 = 0;
-                if (lane == __ffs(b) - 1) base0 = atomicAdd(&d.outbox_count[dst], (unsigned long long)__popc(b));
-                base0 = __shfl_sync(0xffffffffu, base0, __ffs(b) - 1);
-                if ((owners >> dst) & 1u) {
-                    const unsigned long long i = base0 + __popc(b & lt);
-                    if (i < d.outbox_cap) {
-                        unsigned long long *r = reinterpret_cast<unsigned long long *>(d.peer_inbox[dst]) + (size_t)d.part * d.outbox_cap * (KEYW + 1) + i;
-                        r[0] = klo;
-                        if constexpr (KEYW == 2) r[d.outbox_cap] = khi;
-                        r[KEYW * d.outbox_cap] = val;
-                    } else {
-                        c->error = 4;
-                    }
+    }
+}
+
+// Parent forwarding (multi-GPU): every partition that owns a successor of a live parent gets the parent itself (16 or
+// 24 bytes over NVLink, stored straight into its peer-mapped inbox) and generates its own successors from it, instead
+// of receiving them one by one.  One thread per live parent; one counter atomic per (warp, destination).
+template <int KEYW>
+__global__ void __launch_bounds__(256) forward_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
+                                                      const __grid_constant__ OwnerArgs oa)
+{
+    SearchCtrl *c = d.ctrl;
+    if (c->done || c->error) return;
+    const long long live_n = (long long)c->live_n;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (long long base = (long long)blockIdx.x * 256; base < live_n; base += (long long)gridDim.x * 256) {
+        const long long i0 = base + threadIdx.x;
+        unsigned owners = 0;
+        unsigned long long klo = 0, khi = 0, val = 0;
+        if (i0 < live_n) {
+            klo = d.live[i0];
+            if constexpr (KEYW == 2) khi = d.live[d.live_cap + i0];
+            val = d.live[KEYW * d.live_cap + i0];
+            Key<KEYW> key;
+            key.lo = klo;
+            if constexpr (KEYW == 2) key.hi = khi;
+            owners = successor_owners<KEYW>(p, oa, key, d.n_parts, d.part);
+        }
+        for (int dst = 0; dst < d.n_parts; dst++) {
+            const unsigned b = __ballot_sync(0xffffffffu, (owners >> dst) & 1u);
+            if (!b) continue;
+            unsigned long long base0 = 0;
+            if (lane == __ffs(b) - 1) base0 = atomicAdd(&d.outbox_count[dst], (unsigned long long)__popc(b));
+            base0 = __shfl_sync(0xffffffffu, base0, __ffs(b) - 1);
+            if ((owners >> dst) & 1u) {
+                const unsigned long long i = base0 + __popc(b & lt);
+                if (i < d.outbox_cap) {
+                    unsigned long long *r = reinterpret_cast<unsigned long long *>(d.peer_inbox[dst]) + (size_t)d.part * d.outbox_cap * (KEYW + 1) + i;
+                    r[0] = klo;
+                    if constexpr (KEYW == 2) r[d.outbox_cap] = khi;
+                    r[KEYW * d.outbox_cap] = val;
+                } else {
+                    c->error = 4;
                 }
             }
         }
@@ -1716,20 +1732,18 @@ int launch_round(pg_ctx *ctx, int f_limit)
     {
         const long long grid = std::min<long long>((s->batch_target + 255) / 256, (long long)ctx->sm_count * 8);
         const DevSearch d = dev_search(ctx);
-        const OwnerArgs oa = owner_args(ctx);
-        if (s->forward) {
-            if (s->keyw == 1)
-                claim_kernel<1, true><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
-            else
-                claim_kernel<2, true><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
-        } else {
-            if (s->keyw == 1)
-                claim_kernel<1, false><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
-            else
-                claim_kernel<2, false><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
-        }
+        if (s->keyw == 1)
+            claim_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(d);
+        else
+            claim_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(d);
         PG_CUDA(ctx, cudaGetLastError());
-        if (s->forward) { // the forwarded parents' counts follow them at once: the owners' barrier is the next thing on every stream
+        if (s->forward) { // the parents and their counts leave at once: they travel while this partition expands its own
+            const OwnerArgs oa = owner_args(ctx);
+            if (s->keyw == 1)
+                forward_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+            else
+                forward_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+            PG_CUDA(ctx, cudaGetLastError());
             publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(d);
             PG_CUDA(ctx, cudaGetLastError());
         }
