@@ -25,6 +25,7 @@
 // Bound: integer ALU / dependency latency (min-plus; no tensor-core shape).
 // Bytes: one cell written once (4 B, or 2 B when 30*(L1+L2) < 65536).
 #include <algorithm>
+#include <cstdlib>
 
 #include "pg_internal.cuh"
 
@@ -32,15 +33,15 @@ namespace {
 
 constexpr int DP_RING = 256;  // ring entries per warp (power of two)
 constexpr int DP_CHUNK = 8;   // consumer fetch / producer publish granularity (steps)
-constexpr int DP_R = 8;       // rows per lane: a warp's band is 32 * DP_R rows
-constexpr int DP_MAXW = 4;    // warps per CTA: one per SM sub-partition, one 32*DP_R x 32 staging tile each
+// rows per lane (a warp's band is 32 * DP_R rows) x warps per CTA (one 32*DP_R x 32 staging tile each): fewer rows per
+// lane shorten the dependent chain of a step and put more warps on a pair; chosen by pg_launch_pair_dp
 
 enum { NoGap = 0, GapX = 1, GapY = 2 };
 
 // AFFINE = false is the reference's actual cost model (Cost.h:13: GapOpen == GapExtension): the direction state
 // cannot change any value, so a cell is min3(below + gap, right + gap, diag + cost) - two dependent integer ops.
 // AFFINE = true carries the direction of the winning move (PairAlign.cpp:96-134) for open != extension.
-template <typename TC, bool AFFINE>
+template <typename TC, bool AFFINE, int DP_R, int DP_MAXW>
 __global__ void __launch_bounds__(32 * DP_MAXW, 1) pair_dp_kernel(const __grid_constant__ DevProblem p, int warps)
 {
     constexpr int R = DP_R, BAND = 32 * DP_R;
@@ -208,7 +209,8 @@ __global__ void __launch_bounds__(32 * DP_MAXW, 1) pair_dp_kernel(const __grid_c
 
 } // namespace
 
-int pg_launch_pair_dp(pg_ctx *ctx, float *kernel_ms)
+template <int DP_R, int DP_MAXW>
+static int launch_pair_dp_cfg(pg_ctx *ctx, float *kernel_ms)
 {
     int max_bands = 1;
     for (const PairGeom &g : ctx->pairs) max_bands = std::max(max_bands, (g.rows - 1 + 32 * DP_R - 1) / (32 * DP_R));
@@ -227,14 +229,14 @@ int pg_launch_pair_dp(pg_ctx *ctx, float *kernel_ms)
     PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     if (ctx->dp.cell16) {
         if (affine)
-            PG_CUDA(ctx, launch(pair_dp_kernel<uint16_t, true>));
+            PG_CUDA(ctx, launch(pair_dp_kernel<uint16_t, true, DP_R, DP_MAXW>));
         else
-            PG_CUDA(ctx, launch(pair_dp_kernel<uint16_t, false>));
+            PG_CUDA(ctx, launch(pair_dp_kernel<uint16_t, false, DP_R, DP_MAXW>));
     } else {
         if (affine)
-            PG_CUDA(ctx, launch(pair_dp_kernel<int32_t, true>));
+            PG_CUDA(ctx, launch(pair_dp_kernel<int32_t, true, DP_R, DP_MAXW>));
         else
-            PG_CUDA(ctx, launch(pair_dp_kernel<int32_t, false>));
+            PG_CUDA(ctx, launch(pair_dp_kernel<int32_t, false, DP_R, DP_MAXW>));
     }
     PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -244,4 +246,14 @@ int pg_launch_pair_dp(pg_ctx *ctx, float *kernel_ms)
     cudaEventDestroy(e1);
     if (kernel_ms) *kernel_ms = ms;
     return PG_OK;
+}
+
+int pg_launch_pair_dp(pg_ctx *ctx, float *kernel_ms)
+{
+    // measured on B200 (ms at S7 / S8): 8 rows/lane x 4 warps 0.209 / 0.421, 4 x 8 0.170 / 0.361, 2 x 16 0.190 / 0.430
+    const char *e = getenv("PG_DP_CFG");
+    const int cfg = e ? atoi(e) : 1;
+    if (cfg == 0) return launch_pair_dp_cfg<8, 4>(ctx, kernel_ms);
+    if (cfg == 2) return launch_pair_dp_cfg<2, 16>(ctx, kernel_ms);
+    return launch_pair_dp_cfg<4, 8>(ctx, kernel_ms);
 }

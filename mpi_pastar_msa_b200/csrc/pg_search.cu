@@ -690,6 +690,7 @@ constexpr int PLAN_SM = 2048;
 template <int KEYW>
 __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevSearch d)
 {
+    constexpr int PF = 4; // pops per thread, each step of their dependent chains (plan -> pool -> table) issued for all four
     __shared__ uint32_t s_plan[PLAN_SM];
     SearchCtrl *c = d.ctrl;
     const int batch_n = (c->done || c->error) ? 0 : c->batch_n;
@@ -701,45 +702,60 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    for (int base = blockIdx.x * 256; base < batch_n; base += gridDim.x * 256) {
-        const int bi = base + threadIdx.x;
-        bool live = false;
-        unsigned long long klo = 0, khi = 0, val = 0;
-        if (bi < batch_n) {
+    for (int base = blockIdx.x * 256 * PF; base < batch_n; base += gridDim.x * 256 * PF) {
+        int bi[PF], pl[PF];
+        uint32_t slot[PF];
+        unsigned long long old[PF], klo[PF], khi[PF];
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            bi[j] = base + j * 256 + threadIdx.x;
             int lo = 0, hi = plan_n - 1;
-            while (lo < hi) { // last plan entry with offset <= bi
-                const int mid = (lo + hi + 1) >> 1;
-                const uint32_t off = plan_sm ? s_plan[mid] : d.plan[mid].offset;
-                if ((int)off <= bi)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            const PlanEntry pe = d.plan[lo];
-            const uint32_t slot = d.pool[(size_t)pe.unit * UNIT + pe.start + (bi - pe.offset)];
-            unsigned long long *e = d.table + (size_t)slot * (KEYW == 1 ? 2 : 4);
-            // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion
-            const unsigned long long old = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
-            if (!(old & OPEN_BIT)) {
-                live = true;
-                val = ~old;
-                if constexpr (KEYW == 1) {
-                    klo = ld_cg_u64(e) - 1;
-                } else {
-                    klo = ld_cg_u64(e);
-                    khi = ld_cg_u64(e + 1) & ~(1ull << 63);
+            if (bi[j] < batch_n) {
+                while (lo < hi) { // last plan entry with offset <= bi
+                    const int mid = (lo + hi + 1) >> 1;
+                    const uint32_t off = plan_sm ? s_plan[mid] : d.plan[mid].offset;
+                    if ((int)off <= bi[j])
+                        lo = mid;
+                    else
+                        hi = mid - 1;
                 }
             }
+            pl[j] = lo;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, live);
-        unsigned long long wbase = 0;
-        if (lane == 0 && bal) wbase = atomicAdd(&c->live_n, (unsigned long long)__popc(bal));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (live) {
-            unsigned long long *r = d.live + (size_t)(wbase + __popc(bal & lt));
-            r[0] = klo;
-            if constexpr (KEYW == 2) r[d.live_cap] = khi;
-            r[KEYW * d.live_cap] = val;
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            slot[j] = 0;
+            if (bi[j] < batch_n) {
+                const PlanEntry pe = d.plan[pl[j]];
+                slot[j] = d.pool[(size_t)pe.unit * UNIT + pe.start + (bi[j] - pe.offset)];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            old[j] = OPEN_BIT;
+            klo[j] = khi[j] = 0;
+            if (bi[j] < batch_n) {
+                unsigned long long *e = d.table + (size_t)slot[j] * (KEYW == 1 ? 2 : 4);
+                // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion.  The key words
+                // never change once an entry exists, so they are read alongside.
+                old[j] = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
+                klo[j] = ld_cg_u64(e);
+                if constexpr (KEYW == 2) khi[j] = ld_cg_u64(e + 1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            const bool live = !(old[j] & OPEN_BIT);
+            const unsigned bal = __ballot_sync(0xffffffffu, live);
+            unsigned long long wbase = 0;
+            if (lane == 0 && bal) wbase = atomicAdd(&c->live_n, (unsigned long long)__popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (live) {
+                unsigned long long *r = d.live + (size_t)(wbase + __popc(bal & lt));
+                r[0] = KEYW == 1 ? klo[j] - 1 : klo[j];
+                if constexpr (KEYW == 2) r[d.live_cap] = khi[j] & ~(1ull << 63);
+                r[KEYW * d.live_cap] = ~old[j];
+            }
         }
     }
 }
@@ -1730,7 +1746,8 @@ int launch_round(pg_ctx *ctx, int f_limit)
     PG_CUDA(ctx, cudaGetLastError());
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     {
-        const long long grid = std::min<long long>((s->batch_target + 255) / 256, (long long)ctx->sm_count * 8);
+        const long long grid = std::min<long long>((s->batch_target + 1023) / 1024, (long long)ctx->sm_count * 8); // claim: 4 pops per thread
+        const long long fgrid = std::min<long long>((s->batch_target + 255) / 256, (long long)ctx->sm_count * 8);
         const DevSearch d = dev_search(ctx);
         if (s->keyw == 1)
             claim_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(d);
@@ -1740,9 +1757,9 @@ int launch_round(pg_ctx *ctx, int f_limit)
         if (s->forward) { // the parents and their counts leave at once: they travel while this partition expands its own
             const OwnerArgs oa = owner_args(ctx);
             if (s->keyw == 1)
-                forward_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+                forward_kernel<1><<<(unsigned)fgrid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
             else
-                forward_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
+                forward_kernel<2><<<(unsigned)fgrid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
             PG_CUDA(ctx, cudaGetLastError());
             publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(d);
             PG_CUDA(ctx, cudaGetLastError());

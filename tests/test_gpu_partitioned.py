@@ -85,3 +85,73 @@ def test_partitioned_kinase_two_parts(gpu_lib):
     seqs = CASES["kinase"]
     r = partitioned_search(gpu_lib, seqs, 2, 32768, "FZORDER", 12, cap=1 << 26)
     assert r["g"] == 421546
+
+
+def p2p_search(m, seqs, parts, batch, hash_type, shift, mode, cap=1 << 22):
+    """The device-driven P2P rounds (pg_search_round_async / pg_search_insert_inbox_async) with G logical partitions on
+    ONE GPU: every partition's inbox and count array are plain device buffers of this process, so "peer-mapped" is
+    simply their address, and the cross-GPU barrier is a device synchronise.  mode 1 = successor records stored by the
+    expand kernel, mode 2 = parent forwarding (forward_kernel + owner-filtered expansion of the received parents)."""
+    import torch
+    Gs, inbox, counts = [], [], []
+    for r in range(parts):
+        G = m.PastarGPU(seqs)
+        G.build_pair_tables()
+        G.configure_hash(hash_type, shift)
+        G.set_stream(torch.cuda.current_stream().cuda_stream)
+        G.search_begin(parts, r, cap, batch, p2p=mode)
+        Gs.append(G)
+        inbox.append(torch.zeros(2 * parts * G.search_region_bytes(), dtype=torch.uint8, device="cuda"))
+        counts.append(torch.zeros(2 * parts, dtype=torch.int64, device="cuda"))
+    for G in Gs:
+        G.search_set_peers([t.data_ptr() for t in inbox])
+        G.search_set_peer_counts([t.data_ptr() for t in counts], 2)
+    best, rounds = INT_MAX, 0
+    while True:
+        for _ in range(3):  # a few rounds between status checks, as the torchrun driver does
+            for G in Gs:
+                G.search_round_async(best)
+            torch.cuda.synchronize()
+            for G in Gs:
+                G.search_insert_inbox_async()
+            torch.cuda.synchronize()
+            rounds += 1
+        for G in Gs:
+            G.search_sync()
+        st = [G.search_status() for G in Gs]
+        mn = min(s[0] for s in st)
+        best = min(s[1] for s in st)
+        assert rounds < 200000
+        if mn >= best or mn == INT_MAX:
+            break
+    res = {"g": best if best != INT_MAX else -1, "rounds": rounds, "expansions": sum(s[2]["expansions"] for s in st),
+           "generated": sum(s[2]["generated"] for s in st)}
+    for G in Gs:
+        G.search_end()
+        G.close()
+    return res
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name,parts,batch,ht,sh", [
+    ("PF08184", 2, 64, "FZORDER", 3), ("test2", 2, 256, "FSUM", 1), ("fam5x60", 3, 64, "FZORDER", 0),
+    ("fam8x20", 4, 4096, "PZORDER", 1), ("fam4x150", 8, 4096, "FZORDER", 12), ("fam6x80", 5, 512, "PSUM", 2),
+    ("test", 4, 16, "FZORDER", 1), ("fam5x60", 16, 1024, "FZORDER", 2)])
+def test_p2p_modes_optimal_cost(gpu_lib, name, parts, batch, ht, sh, mode):
+    seqs = CASES[name]
+    ref = KNOWN_OPT.get(name) or O.Problem(seqs).astar(want_rows=False)["g"]
+    r = p2p_search(gpu_lib, seqs, parts, batch, ht, sh, mode)
+    assert r["g"] == ref, (name, parts, mode, r)
+
+
+def test_forwarding_generates_each_successor_once(gpu_lib):
+    """Parent forwarding must neither lose nor duplicate successors: every valid successor of an expansion is counted
+    exactly once, by its owner, so successors per expansion must match the successor-record mode (the expansion counts
+    themselves may differ by a few reopened nodes: the insertion order inside a round is not deterministic)."""
+    seqs = CASES["fam5x60"]
+    r1 = p2p_search(gpu_lib, seqs, 4, 1024, "FZORDER", 2, 1)
+    r2 = p2p_search(gpu_lib, seqs, 4, 1024, "FZORDER", 2, 2)
+    assert r1["g"] == r2["g"]
+    assert abs(r1["expansions"] - r2["expansions"]) <= 0.05 * r1["expansions"]
+    per1, per2 = r1["generated"] / r1["expansions"], r2["generated"] / r2["expansions"]
+    assert abs(per1 - per2) <= 0.01 * per1, (r1, r2)
