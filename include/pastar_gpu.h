@@ -159,6 +159,16 @@ typedef struct {
  * sum(lens)+1 bytes receive the aligned sequences (backtrace.cpp:77-109). */
 int pg_search(pg_ctx *ctx, const pg_search_config *cfg, pg_result *res, char *const *rows);
 
+/* The same search hash-partitioned over n_gpus GPUs of one box, driven by ONE host process: ctxs[i] is a context
+ * created on device i (same sequences, weights and hash configuration; pair tables built).  Replaces pa_star with
+ * threads x MPI ranks (PAStar.cpp:626-673), the sender / receiver / decoder threads (pastar_functions/*.cpp) and
+ * check_stop's allreduces (PAStar.cpp:502-519): one partition per GPU (owner = Coord::get_id(n_gpus)), parent
+ * forwarding over peer-mapped inboxes (NVLink), cross-GPU ordering by stream-wait events, no NCCL.  total = summed
+ * counters + final score + alignment rows; parts (may be NULL) = n_gpus per-partition counters (the reference's
+ * per-thread rows of "Total nodes count:").  cfg->n_parts / part / reserved are ignored. */
+int pg_multi_search(pg_ctx *const *ctxs, int n_gpus, const pg_search_config *cfg, pg_result *total, pg_result *parts,
+                    char *const *rows);
+
 /* Step-wise form for hash-partitioned multi-GPU drivers (one context per GPU,
  * the exchange between the two calls is the driver's: NCCL all-to-all).
  * Replaces worker_inner's expand + reconciliation (PAStar.cpp:319-401) and

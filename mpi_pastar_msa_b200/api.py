@@ -92,6 +92,7 @@ def load_library():
         "pg_search_round_async": ([vp, C.c_int32], i32),
         "pg_search_insert_inbox_async": ([vp], i32),
         "pg_search_sync": ([vp], i32),
+        "pg_multi_search": ([C.POINTER(vp), i32, C.POINTER(SearchConfig), C.POINTER(Result), C.POINTER(Result), C.POINTER(C.c_char_p)], i32),
         "pg_search_region_bytes": ([vp], i64),
         "pg_search_outbox_capacity": ([vp], i64),
         "pg_search_outbox_counts_dev": ([vp, C.POINTER(vp)], i32),
@@ -109,7 +110,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -165,6 +166,27 @@ def bench_random_gather(nbytes, device=-1):
     if rc:
         raise PastarError(rc, "pg_bench_random_gather")
     return out.value
+
+
+def multi_search(gpus, table_capacity=0, batch_target=0, max_expansions=0, rounds_per_sync=0, want_rows=True):
+    """pg_multi_search: one hash-owned partition per context in `gpus` (PastarGPU objects with their pair tables built and
+    the same hash configuration; normally one per device, but contexts on one device work too), driven by this process.
+    Returns (total dict, list of per-partition dicts)."""
+    L = load_library()
+    g0 = gpus[0]
+    cfg = SearchConfig(len(gpus), 0, table_capacity, batch_target, max_expansions, rounds_per_sync, 0)
+    res, parts = Result(), (Result * len(gpus))()
+    handles = (C.c_void_p * len(gpus))(*[g.h for g in gpus])
+    rows, bufs = None, None
+    if want_rows:
+        total = sum(g0.lens) + 1
+        bufs = [C.create_string_buffer(total) for _ in range(g0.n)]
+        rows = (C.c_char_p * g0.n)(*[C.cast(b, C.c_char_p) for b in bufs])
+    g0._ck(L.pg_multi_search(handles, len(gpus), C.byref(cfg), C.byref(res), parts, rows))
+    d = res.as_dict()
+    if want_rows and res.finished:
+        d["rows"] = [b.value.decode() for b in bufs]
+    return d, [p.as_dict() for p in parts]
 
 
 def host_weights(seqs):

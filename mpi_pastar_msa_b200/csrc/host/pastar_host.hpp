@@ -161,9 +161,37 @@ class HeuristicHPair {
         check(rc, "pg_ctx_create");
         check(pg_build_pair_tables(ctx, &tables_ms), "pg_build_pair_tables");
         std::cout << "done!\n";
+        wint_keep = wint;
+    }
+    // One more context per additional GPU: the reference recomputes the heuristic on every MPI rank
+    // (HeuristicHPair.cpp:47-67 runs everywhere); here every device builds its own copy of the pair tables.
+    std::vector<pg_ctx *> contexts(int gpus)
+    {
+        Sequences *seq = Sequences::getInstance();
+        const int n = Sequences::get_seq_num();
+        std::vector<const char *> ptr(n);
+        std::vector<int> len(n);
+        for (int i = 0; i < n; i++) {
+            ptr[i] = seq->get_seq(i).data();
+            len[i] = (int)seq->get_seq(i).size();
+        }
+        while ((int)more.size() + 1 < gpus) {
+            pg_ctx *c = nullptr;
+            const int dev = (int)more.size() + 1;
+            int rc = pg_ctx_create(n, ptr.data(), len.data(), nullptr, Cost::GapOpen, Cost::GapExtension, Cost::GapGap, wint_keep.data(), dev, &c);
+            if (rc != PG_OK) throw GpuError(rc, "pg_ctx_create on device " + std::to_string(dev) + " failed (are there that many GPUs?)");
+            more.push_back(c);
+            rc = pg_build_pair_tables(c, nullptr);
+            if (rc != PG_OK) throw GpuError(rc, std::string("pg_build_pair_tables: ") + pg_last_error(c));
+        }
+        std::vector<pg_ctx *> all{ctx};
+        for (int i = 0; i + 1 < gpus; i++) all.push_back(more[i]);
+        return all;
     }
     void destroyInstance()
     {
+        for (pg_ctx *c : more) pg_ctx_destroy(c);
+        more.clear();
         if (ctx) pg_ctx_destroy(ctx);
         ctx = nullptr;
     }
@@ -196,6 +224,8 @@ class HeuristicHPair {
     std::vector<float> flat;
     std::vector<float *> rows;
     std::vector<std::vector<int32_t>> tables;
+    std::vector<int32_t> wint_keep;
+    std::vector<pg_ctx *> more; // contexts on devices 1 .. gpus-1
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -389,6 +419,7 @@ class PAStar {
         std::cout << "Running PAStar with: " << options.totalThreads << " threads (" << options.mpiCommSize << " machines with "
                   << options.threads_num << " threads each)," << Coord<N>::get_hash_name() << " hash, " << Coord<N>::get_hash_shift()
                   << " shift.\n";
+        if (options.gpus > 1) std::cout << "Hash-owned partitions: " << options.gpus << " (one per GPU)\n";
         HeuristicHPair *h = HeuristicHPair::getInstance();
         pg_search_config cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -397,14 +428,23 @@ class PAStar {
         cfg.table_capacity = options.table_capacity;
         cfg.max_expansions = options.max_expansions;
         pg_result res;
+        const int gpus = options.gpus > 0 ? options.gpus : 1;
+        std::vector<pg_result> parts(gpus);
         size_t total = 1;
         for (int i = 0; i < N; i++) total += coord_final[i];
         std::vector<std::vector<char>> bufs(N, std::vector<char>(total));
         std::vector<char *> rowp(N);
         for (int i = 0; i < N; i++) rowp[i] = bufs[i].data();
-        {
+        if (gpus == 1) {
             TimeCounter t("Phase 2: PA-Star running time: ");
             h->check(pg_search(h->ctx, &cfg, &res, rowp.data()), "pg_search");
+            parts[0] = res;
+        } else {
+            // one hash-owned partition per GPU (the reference: one per thread x MPI rank, PAStar.cpp:107-117)
+            std::vector<pg_ctx *> ctxs = h->contexts(gpus);
+            for (pg_ctx *c : ctxs) h->check(pg_configure_hash(c, (int)options.hash_type, options.hash_shift), "pg_configure_hash");
+            TimeCounter t("Phase 2: PA-Star running time: ");
+            h->check(pg_multi_search(ctxs.data(), gpus, &cfg, &res, parts.data(), rowp.data()), "pg_multi_search");
         }
         if (!res.finished) {
             std::cout << "Search stopped at the expansion budget: " << res.expansions << " expansions, no alignment.\n";
@@ -422,8 +462,9 @@ class PAStar {
         }
         // print_nodes_count, PAStar.cpp:591-619: one "tid" row per partition
         std::cout << "Total nodes count:" << std::endl;
-        std::cout << "tid 0\tOpenList:" << res.open_size << "\tClosedList:" << res.closed_size << "\tReopen:" << res.reopen
-                  << "\tTotal: " << res.pops << std::endl;
+        for (int i = 0; i < gpus; i++)
+            std::cout << "tid " << i << "\tOpenList:" << parts[i].open_size << "\tClosedList:" << parts[i].closed_size << "\tReopen:" << parts[i].reopen
+                      << "\tTotal: " << parts[i].pops << std::endl;
         std::cout << "Sum\tOpenList:" << res.open_size << "\tClosedList:" << res.closed_size << "\tReopen:" << res.reopen
                   << "\tTotal: " << res.pops << std::endl;
         std::cout << "GPU: " << res.expansions << " expansions, " << res.generated << " successors, " << res.rounds << " rounds, "

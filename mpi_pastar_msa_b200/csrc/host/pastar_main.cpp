@@ -202,8 +202,8 @@ int main(int argc, char *argv[])
     PAStarOpt opt;
     std::string filename;
     if (msa_pastar_options(argc, argv, filename, opt) != 0) return 1; // the reference MPI_Aborts with 1 here
-    if (opt.gpus != 1) {
-        std::cerr << "Fatal error: this binary drives one GPU; multi-GPU runs use the torchrun driver (mpi_pastar_msa_b200.dist)\n";
+    if (opt.gpus < 1 || opt.gpus > 16) {
+        std::cerr << "Fatal error: --gpus must be between 1 and 16\n";
         return 1;
     }
     opt.mpiRank = 0;

@@ -2282,3 +2282,222 @@ extern "C" int pg_search(pg_ctx *ctx, const pg_search_config *cfg_in, pg_result 
     res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return PG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pg_multi_search: the hash-partitioned search over G GPUs of one box, driven by ONE host process (the pastar CLI).
+// Replaces PAStar<N>::pa_star with threads x MPI ranks (PAStar.cpp:626-673) plus sender / receiver / decoder threads
+// (pastar_functions/*.cpp) and check_stop's allreduces (PAStar.cpp:502-519): one partition per GPU, parent forwarding
+// over peer-mapped inboxes (cudaDeviceEnablePeerAccess: NVLink), the per-round cross-GPU barrier is a set of
+// cudaStreamWaitEvent edges (no host blocking), the stop test runs every few rounds on the host from the partitions'
+// control blocks.  torch / NCCL are not involved.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+int census_ctx(pg_ctx *ctx, int64_t *open_size, int64_t *closed_size)
+{
+    SearchState *s = ctx->search;
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d_cnt = (unsigned long long *)s->d_trace;
+    PG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
+    if (s->keyw == 1)
+        census_kernel<1><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
+    else
+        census_kernel<2><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
+    unsigned long long h[2];
+    PG_CUDA(ctx, cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *open_size = (int64_t)h[0];
+    *closed_size = (int64_t)h[1];
+    return PG_OK;
+}
+} // namespace
+
+extern "C" int pg_multi_search(pg_ctx *const *ctxs, int n_gpus, const pg_search_config *cfg_in, pg_result *total, pg_result *parts,
+                               char *const *rows)
+{
+    if (!ctxs || n_gpus < 1 || n_gpus > 16 || !total) return PG_ERR_ARG;
+    for (int i = 0; i < n_gpus; i++)
+        if (!ctxs[i]) return PG_ERR_ARG;
+    pg_ctx *c0 = ctxs[0];
+    if (n_gpus == 1) {
+        int rc = pg_search(c0, cfg_in, total, rows);
+        if (rc == PG_OK && parts) parts[0] = *total;
+        return rc;
+    }
+    pg_search_config cfg;
+    if (cfg_in)
+        cfg = *cfg_in;
+    else
+        memset(&cfg, 0, sizeof(cfg));
+    memset(total, 0, sizeof(*total));
+    total->g = total->f = -1;
+    auto t0 = std::chrono::steady_clock::now();
+    const int G = n_gpus;
+    std::vector<void *> inbox(G, nullptr), counts(G, nullptr);
+    std::vector<cudaEvent_t> ev(G, nullptr);
+    int rc = PG_OK;
+    auto cleanup = [&]() {
+        for (int i = 0; i < G; i++) {
+            cudaSetDevice(ctxs[i]->device);
+            if (ctxs[i]->search) cudaStreamSynchronize(ctxs[i]->stream);
+            cudaFree(inbox[i]);
+            cudaFree(counts[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+    };
+#define MG_CHECK(i, expr)                                  \
+    do {                                                   \
+        rc = (expr);                                       \
+        if (rc != PG_OK) {                                 \
+            if (ctxs[i] != c0) c0->err = ctxs[i]->err;     \
+            cleanup();                                     \
+            return rc;                                     \
+        }                                                  \
+    } while (0)
+#define MG_CUDA(i, expr)                                                                                         \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess) {                                                                                \
+            rc = pg_fail(c0, PG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+            cleanup();                                                                                           \
+            return rc;                                                                                           \
+        }                                                                                                        \
+    } while (0)
+
+    // ---- peer access between every pair of devices; one search state, inbox and count array per device
+    for (int i = 0; i < G; i++) {
+        MG_CUDA(i, cudaSetDevice(ctxs[i]->device));
+        for (int j = 0; j < G; j++) {
+            if (ctxs[j]->device == ctxs[i]->device) continue;
+            int can = 0;
+            MG_CUDA(i, cudaDeviceCanAccessPeer(&can, ctxs[i]->device, ctxs[j]->device));
+            if (!can) {
+                rc = pg_fail(c0, PG_ERR_UNSUPPORTED, "pg_multi_search: the devices cannot access each other's memory");
+                cleanup();
+                return rc;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MG_CUDA(i, e);
+            cudaGetLastError();
+        }
+    }
+    for (int i = 0; i < G; i++) {
+        pg_search_config ci = cfg;
+        ci.n_parts = G;
+        ci.part = i;
+        ci.reserved = 2; // parent forwarding
+        MG_CHECK(i, pg_search_begin(ctxs[i], &ci));
+        MG_CUDA(i, cudaSetDevice(ctxs[i]->device));
+        const size_t bytes = 2 * (size_t)G * ctxs[i]->search->region_bytes;
+        MG_CUDA(i, cudaMalloc(&inbox[i], bytes));
+        MG_CUDA(i, cudaMalloc(&counts[i], 2 * (size_t)G * 8));
+        MG_CUDA(i, cudaMemset(counts[i], 0, 2 * (size_t)G * 8));
+        MG_CUDA(i, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < G; i++) {
+        MG_CHECK(i, pg_search_set_peers(ctxs[i], inbox.data(), G));
+        MG_CHECK(i, pg_search_set_peer_counts(ctxs[i], counts.data(), G, 2));
+    }
+
+    // ---- rounds
+    const int per_sync = cfg.rounds_per_sync > 0 ? cfg.rounds_per_sync : 4;
+    int best = INT_MAX, min_open = INT_MAX;
+    bool finished = false;
+    std::vector<pg_result> pr(G);
+    for (;;) {
+        for (int r = 0; r < per_sync; r++) {
+            for (int i = 0; i < G; i++) MG_CHECK(i, pg_search_round_async(ctxs[i], best));
+            // barrier: nobody reads its inbox before every partition's forward + publish kernels of this round are done
+            for (int i = 0; i < G; i++) {
+                MG_CUDA(i, cudaSetDevice(ctxs[i]->device));
+                MG_CUDA(i, cudaEventRecord(ev[i], ctxs[i]->stream));
+            }
+            for (int j = 0; j < G; j++) {
+                MG_CUDA(j, cudaSetDevice(ctxs[j]->device));
+                for (int i = 0; i < G; i++)
+                    if (i != j) MG_CUDA(j, cudaStreamWaitEvent(ctxs[j]->stream, ev[i], 0));
+            }
+            for (int i = 0; i < G; i++) MG_CHECK(i, pg_search_insert_inbox_async(ctxs[i]));
+        }
+        // stop test (PAStar.cpp:410-547): nothing is in flight once every stream has drained
+        for (int i = 0; i < G; i++) MG_CHECK(i, pg_search_sync(ctxs[i]));
+        min_open = INT_MAX;
+        int64_t expansions = 0;
+        for (int i = 0; i < G; i++) {
+            int32_t mn = 0, bg = 0;
+            MG_CHECK(i, pg_search_status(ctxs[i], &mn, &bg, &pr[i]));
+            min_open = std::min(min_open, (int)mn);
+            best = std::min(best, (int)bg);
+            expansions += pr[i].expansions;
+        }
+        if (min_open >= best || min_open == INT_MAX) {
+            finished = best != INT_MAX;
+            break;
+        }
+        if (cfg.max_expansions > 0 && expansions >= cfg.max_expansions) break;
+    }
+
+    // ---- results: counters per partition and summed; open / closed census (PAStar.cpp:591-619)
+    for (int i = 0; i < G; i++) {
+        MG_CHECK(i, census_ctx(ctxs[i], &pr[i].open_size, &pr[i].closed_size));
+        pr[i].finished = finished ? 1 : 0;
+        total->pops += pr[i].pops;
+        total->expansions += pr[i].expansions;
+        total->generated += pr[i].generated;
+        total->reopen += pr[i].reopen;
+        total->open_size += pr[i].open_size;
+        total->closed_size += pr[i].closed_size;
+        total->probed += pr[i].probed;
+        total->pushed += pr[i].pushed;
+        total->inserted += pr[i].inserted;
+        total->survivors += pr[i].survivors;
+        total->rounds = pr[i].rounds;
+        if (parts) parts[i] = pr[i];
+    }
+    total->finished = finished ? 1 : 0;
+    if (finished) {
+        total->g = total->f = best;
+        // distributed backtrace (PAStarDistributedBacktrace.cpp:18-214): the owner of each coordinate answers
+        const int n = c0->n;
+        std::vector<uint16_t> pos(n);
+        for (int i = 0; i < n; i++) pos[i] = (uint16_t)c0->len[i];
+        std::vector<uint32_t> masks;
+        for (;;) {
+            bool origin = true;
+            for (int i = 0; i < n; i++) origin = origin && pos[i] == 0;
+            if (origin) break;
+            uint32_t own = 0;
+            MG_CHECK(0, pg_owner(c0, pos.data(), 1, G, &own));
+            int32_t found = 0, g = 0, parenti = 0;
+            MG_CHECK((int)own, pg_search_lookup(ctxs[own], pos.data(), &found, &g, &parenti));
+            if (!found || parenti == 0) {
+                rc = pg_fail(c0, PG_ERR_STATE, "backtrace lost the parent chain");
+                cleanup();
+                return rc;
+            }
+            masks.push_back((uint32_t)parenti);
+            for (int i = 0; i < n; i++) pos[i] = (uint16_t)(pos[i] - ((parenti >> i) & 1));
+        }
+        const int cols = (int)masks.size();
+        total->align_len = cols;
+        if (rows) {
+            std::vector<int> at(n, 0);
+            for (int i = 0; i < n; i++) rows[i][cols] = 0;
+            for (int c = 0; c < cols; c++) {
+                const uint32_t mask = masks[cols - 1 - c];
+                for (int i = 0; i < n; i++) rows[i][c] = ((mask >> i) & 1) ? c0->seqs[i][at[i]++] : '-';
+            }
+        }
+    }
+    for (int i = 0; i < G; i++) {
+        pr[i].g = total->g;
+        pr[i].f = total->f;
+        if (parts) parts[i] = pr[i];
+    }
+    cleanup();
+    for (int i = 0; i < G; i++) pg_search_end(ctxs[i]);
+    total->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    total->kernel_ms = total->seconds * 1e3;
+    return PG_OK;
+#undef MG_CHECK
+#undef MG_CUDA
+}

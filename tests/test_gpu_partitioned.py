@@ -155,3 +155,28 @@ def test_forwarding_generates_each_successor_once(gpu_lib):
     assert abs(r1["expansions"] - r2["expansions"]) <= 0.05 * r1["expansions"]
     per1, per2 = r1["generated"] / r1["expansions"], r2["generated"] / r2["expansions"]
     assert abs(per1 - per2) <= 0.01 * per1, (r1, r2)
+
+
+@pytest.mark.parametrize("name,parts,batch,ht,sh", [
+    ("PF08184", 2, 64, "FZORDER", 3), ("fam5x60", 3, 256, "FZORDER", 0), ("fam8x20", 4, 4096, "PZORDER", 1),
+    ("fam4x150", 8, 4096, "FZORDER", 12), ("fam6x80", 5, 512, "FSUM", 2)])
+def test_multi_search_one_process(gpu_lib, name, parts, batch, ht, sh):
+    """pg_multi_search (what `pastar -g G` calls): G partitions driven by one process; on this one-GPU box the G contexts
+    share the device, the exchange code path (forwarded parents, event barrier, owner lookups for the backtrace) is the
+    same.  Optimal cost, a valid alignment, and per-partition counters that add up."""
+    seqs = CASES[name]
+    ref = KNOWN_OPT.get(name) or O.Problem(seqs).astar(want_rows=False)["g"]
+    Gs = []
+    for _ in range(parts):
+        G = gpu_lib.PastarGPU(seqs)
+        G.build_pair_tables()
+        G.configure_hash(ht, sh)
+        Gs.append(G)
+    tot, per = gpu_lib.multi_search(Gs, table_capacity=1 << 22, batch_target=batch)
+    assert tot["finished"] == 1 and tot["g"] == ref, tot
+    w = gpu_lib.host_weights(seqs).astype(np.int32)
+    assert weighted_sp_score(seqs, w, tot["rows"]) == ref
+    assert sum(p["expansions"] for p in per) == tot["expansions"] and sum(p["pops"] for p in per) == tot["pops"]
+    assert tot["closed_size"] == sum(p["closed_size"] for p in per) > 0
+    for G in Gs:
+        G.close()
