@@ -1,10 +1,11 @@
 #!/bin/bash
-# ncu captures of one steady-state launch of each kernel of the search round (S7, batch 2^20, 16 GiB table).
-# usage (under gpurun): bash tools/ncu_round.sh <tag> [kernel-regex ...]
+# ncu captures of one steady-state launch of each kernel of the search round (S7, batch 2^20, 16 GiB table), plus the
+# launch list of 40 steady-state launches.   usage (under gpurun): bash tools/ncu_round.sh <tag> [kernel-regex ...]
 tag=$1; shift
 kernels=${@:-"insert_kernel claim_kernel expand_probe_kernel"}
 cmd="python tools/search_once.py s7 1048576 60000000 1073741824"
 $cmd > gpurun_out/plain_$tag.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'select_kernel|claim_kernel|expand_probe_kernel|insert_kernel' -s 1600 -c 40 --csv --log-file gpurun_out/launches_$tag.csv $cmd > gpurun_out/ncu_launches_$tag.log 2>&1
 for k in $kernels; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 420 -c 1 -f -o gpurun_out/prof_${tag}_$k $cmd > gpurun_out/ncu_${tag}_$k.log 2>&1
 done
