@@ -255,5 +255,6 @@ int pg_launch_pair_dp(pg_ctx *ctx, float *kernel_ms)
     const int cfg = e ? atoi(e) : 1;
     if (cfg == 0) return launch_pair_dp_cfg<8, 4>(ctx, kernel_ms);
     if (cfg == 2) return launch_pair_dp_cfg<2, 16>(ctx, kernel_ms);
+    if (cfg == 3) return launch_pair_dp_cfg<1, 32>(ctx, kernel_ms);
     return launch_pair_dp_cfg<4, 8>(ctx, kernel_ms);
 }

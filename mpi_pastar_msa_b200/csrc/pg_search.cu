@@ -692,6 +692,8 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
 {
     constexpr int PF = 4; // pops per thread, each step of their dependent chains (plan -> pool -> table) issued for all four
     __shared__ uint32_t s_plan[PLAN_SM];
+    __shared__ int s_wtot[8];
+    __shared__ unsigned long long s_base;
     SearchCtrl *c = d.ctrl;
     const int batch_n = (c->done || c->error) ? 0 : c->batch_n;
     if (batch_n == 0) return;
@@ -743,19 +745,38 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
                 if constexpr (KEYW == 2) khi[j] = ld_cg_u64(e + 1);
             }
         }
+        // compaction: one atomic on the live counter per CTA sweep (a per-warp atomic on that single address was 60 % of
+        // this kernel's stall samples): warp totals -> shared-memory prefix -> one reservation for the CTA
+        unsigned bal[PF];
+        int wtot = 0;
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            const bool live = !(old[j] & OPEN_BIT);
-            const unsigned bal = __ballot_sync(0xffffffffu, live);
-            unsigned long long wbase = 0;
-            if (lane == 0 && bal) wbase = atomicAdd(&c->live_n, (unsigned long long)__popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (live) {
-                unsigned long long *r = d.live + (size_t)(wbase + __popc(bal & lt));
+            bal[j] = __ballot_sync(0xffffffffu, !(old[j] & OPEN_BIT));
+            wtot += __popc(bal[j]);
+        }
+        if (lane == 0) s_wtot[threadIdx.x >> 5] = wtot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; w++) {
+                const int t = s_wtot[w];
+                s_wtot[w] = tot;
+                tot += t;
+            }
+            s_base = tot ? atomicAdd(&c->live_n, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long wbase = s_base + (unsigned long long)s_wtot[threadIdx.x >> 5];
+        __syncthreads(); // s_wtot / s_base are rewritten by the next sweep
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            if (!(old[j] & OPEN_BIT)) {
+                unsigned long long *r = d.live + (size_t)(wbase + __popc(bal[j] & lt));
                 r[0] = KEYW == 1 ? klo[j] - 1 : klo[j];
                 if constexpr (KEYW == 2) r[d.live_cap] = khi[j] & ~(1ull << 63);
                 r[KEYW * d.live_cap] = ~old[j];
             }
+            wbase += __popc(bal[j]);
         }
     }
 }
@@ -1209,8 +1230,25 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     int min_b = INT_MAX;
     const int limit = min(c->prune_limit, c->best_goal);
+    __shared__ unsigned long long s_walk[8 * RING_CAP * XW];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned long long *wq = s_walk + (size_t)(threadIdx.x >> 5) * RING_CAP * XW;
+    unsigned qhead = 0, qtail = 0; // warp-uniform
+    auto walk_one = [&](const unsigned long long *it) {
+        Key<KEYW> k;
+        k.lo = it[0];
+        if constexpr (KEYW == 2) k.hi = it[1];
+        const unsigned long long g_f = it[KEYW], m = it[KEYW + 1];
+        const unsigned fl = upsert_from<KEYW>(d, k, m >> 32, (int)(unsigned)(g_f >> 32), (int)(unsigned)g_f, (int)(m & 0xffffu));
+        cn.inserted += fl & UPS_INSERTED;
+        cn.pushed += (fl >> 1) & 1u;
+        cn.reopen += (fl >> 2) & 1u;
+        if (fl & UPS_PUSHED) min_b = min(min_b, (int)(unsigned)g_f - c->f0);
+    };
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n; i0 += stride * PF) {
+    // the trip count is warp-uniform: the deferred ring is a warp-level structure
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * PF) {
         Key<KEYW> key[PF];
         unsigned long long gf[PF], lk[PF], lv[PF], lw[KEYW == 2 ? PF : 1];
         uint32_t st[PF];
@@ -1323,17 +1361,29 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < PF; j++)
             if (state[j] == PUSH) bucket_place(d, bk[j], st[j], lk[j]);
-        // ---- everything else, one at a time
+        // ---- everything else goes to the warp's deferred ring and is handled 32 at a time with every lane busy (about
+        //      1 % of the records: done in place, one straggling lane would stall its warp in most iterations)
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            if (state[j] != WALK) continue;
-            const unsigned fl = upsert_from<KEYW>(d, key[j], st[j], (int)(unsigned)(gf[j] >> 32), (int)(unsigned)gf[j], (int)mk[j]);
-            cn.inserted += fl & UPS_INSERTED;
-            cn.pushed += (fl >> 1) & 1u;
-            cn.reopen += (fl >> 2) & 1u;
-            if (fl & UPS_PUSHED) min_b = min(min_b, (int)(unsigned)gf[j] - c->f0);
+            const unsigned wb = __ballot_sync(0xffffffffu, state[j] == WALK);
+            if (!wb) continue;
+            if (state[j] == WALK) {
+                unsigned long long *q = wq + (size_t)((qtail + __popc(wb & lt)) & (RING_CAP - 1)) * XW;
+                q[0] = key[j].lo;
+                if constexpr (KEYW == 2) q[1] = key[j].hi;
+                q[KEYW] = gf[j];
+                q[KEYW + 1] = ((unsigned long long)st[j] << 32) | (unsigned long long)mk[j];
+            }
+            qtail += __popc(wb);
+            __syncwarp();
+            if (qtail - qhead >= 32u) {
+                walk_one(wq + (size_t)((qhead + lane) & (RING_CAP - 1)) * XW);
+                qhead += 32u;
+                __syncwarp();
+            }
         }
     }
+    if (lane < (int)(qtail - qhead)) walk_one(wq + (size_t)((qhead + lane) & (RING_CAP - 1)) * XW);
     // A node may have a lower f than anything open here (it came from another partition, or this partition's open
     // list ran empty): pull the select cursor back so the next round sees it.
     for (int o = 16; o; o >>= 1) min_b = min(min_b, __shfl_down_sync(0xffffffffu, min_b, o));
