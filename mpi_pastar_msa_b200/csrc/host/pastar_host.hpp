@@ -399,6 +399,7 @@ struct PAStarOpt { // PAStar.h:87-112, plus the GPU-side knobs (new, do not chan
     int mpiRank = 0, mpiCommSize = 1, mpiMin = 0, mpiMax = 1, totalThreads = 1;
     int gpus = 1;
     long long batch = 0, table_capacity = 0, max_expansions = 0;
+    std::string metrics_json; // --metrics_json FILE: counters of the run as one JSON object (PAStarSyncData.cpp's gather, machine-readable)
 };
 
 int read_fasta_file(const std::string &name);
@@ -471,6 +472,25 @@ class PAStar {
                   << std::fixed << std::setprecision(3) << res.kernel_ms << " ms on device ("
                   << (res.kernel_ms > 0 ? res.expansions / res.kernel_ms / 1e3 : 0.0) << " M expansions/s); pairwise tables "
                   << h->tables_ms << " ms" << std::endl;
+        if (!options.metrics_json.empty()) {
+            std::ofstream js(options.metrics_json);
+            auto one = [&](const pg_result &r) {
+                js << "{\"pops\": " << r.pops << ", \"expansions\": " << r.expansions << ", \"generated\": " << r.generated
+                   << ", \"probed\": " << r.probed << ", \"pushed\": " << r.pushed << ", \"inserted\": " << r.inserted
+                   << ", \"reopen\": " << r.reopen << ", \"open_size\": " << r.open_size << ", \"closed_size\": " << r.closed_size << "}";
+            };
+            js << "{\"finished\": " << res.finished << ", \"g\": " << res.g << ", \"f\": " << res.f << ", \"align_len\": " << res.align_len
+               << ", \"rounds\": " << res.rounds << ", \"gpus\": " << gpus << ", \"search_ms\": " << res.kernel_ms
+               << ", \"pair_tables_ms\": " << h->tables_ms << ", \"hash_type\": \"" << Coord<N>::get_hash_name() << "\", \"hash_shift\": "
+               << Coord<N>::get_hash_shift() << ", \"total\": ";
+            one(res);
+            js << ", \"partitions\": [";
+            for (int i = 0; i < gpus; i++) {
+                if (i) js << ", ";
+                one(parts[i]);
+            }
+            js << "]}\n";
+        }
         return 0;
     }
 };

@@ -1,7 +1,7 @@
 // pastar — drop-in CLI for the reference's ./bin/pastar (pastar/msa_pastar_main.cpp:56-193), GPU path.
 //
 //   pastar [-t N] [-s SHIFT] [-y FZORDER|FSUM|PZORDER|PSUM] [-v] [-h] [--memory_debug] file.fasta
-//   new, optional: [-g/--gpus N] [--batch K] [--table_capacity SLOTS] [--max_expansions E]
+//   new, optional: [-g/--gpus N] [--batch K] [--table_capacity SLOTS] [--max_expansions E] [--metrics_json FILE]
 //
 // Same flags, exit codes (0 ok, 1 usage / not a regular file, -1 on exception) and stdout format as the reference
 // (phase timers, "Final Score:", "Similarity:", wrapped alignment, "Total nodes count:" table).  No MPI: the
@@ -60,6 +60,7 @@ static void usage(const char *argv0)
               << "  --batch arg                   frontier nodes popped per round\n"
               << "  --table_capacity arg          closed/open table slots\n"
               << "  --max_expansions arg          stop after this many expansions\n"
+              << "  --metrics_json arg            write the run's counters (total and per partition) as JSON\n"
               << std::endl;
 }
 
@@ -91,6 +92,7 @@ static int options_core(int argc, char *argv[], std::string &filename, PAStarOpt
         else if (a.compare(0, 7, "--batch") == 0) opt.batch = std::stoll(value(i, a, "batch"));
         else if (a.compare(0, 16, "--table_capacity") == 0) opt.table_capacity = std::stoll(value(i, a, "table_capacity"));
         else if (a.compare(0, 16, "--max_expansions") == 0) opt.max_expansions = std::stoll(value(i, a, "max_expansions"));
+        else if (a.compare(0, 14, "--metrics_json") == 0) opt.metrics_json = value(i, a, "metrics_json");
         else if (!a.empty() && a[0] == '-' && a.size() > 1) throw std::invalid_argument("unrecognised option '" + a + "'");
         else {
             filename = a; // file.fasta is position independent

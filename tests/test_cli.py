@@ -75,3 +75,17 @@ def test_output_format_and_score(tmp_path, name, args):
     assert lines[i] == "Total nodes count:"
     assert re.match(r"tid 0\tOpenList:\d+\tClosedList:\d+\tReopen:\d+\tTotal: \d+$", lines[i + 1])
     assert re.match(r"Sum\tOpenList:\d+\tClosedList:\d+\tReopen:\d+\tTotal: \d+$", lines[i + 2])
+
+
+@pytest.mark.gpu
+def test_metrics_json_sidecar(tmp_path):
+    """--metrics_json: the counters the reference gathers on rank 0 (PAStarSyncData.cpp:13-116) as a JSON object."""
+    import json
+    fa, js = tmp_path / "k.fasta", tmp_path / "m.json"
+    write_fasta(str(fa), CASES["fam5x60"])
+    r = run(["--metrics_json", str(js), str(fa)])
+    assert r.returncode == 0, r.stderr.decode()
+    d = json.load(open(js))
+    assert d["finished"] == 1 and d["gpus"] == 1 and len(d["partitions"]) == 1
+    assert d["total"]["expansions"] == d["partitions"][0]["expansions"] > 0
+    assert "Final Score:" in r.stdout.decode() and ("g - %d " % d["g"]) in r.stdout.decode()
