@@ -13,8 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 PHASE = bool(os.environ.get("PG_PHASE_TIMING"))  # instrumented variant: per-phase cycle counters in the expand kernel
-OBJ = os.path.join(HERE, "build_phase" if PHASE else "build")
-LIB = os.path.join(HERE, "lib", "libpastar_gpu_phase.so" if PHASE else "libpastar_gpu.so")
+# experiment variants: PG_VARIANT=name PG_EXTRA_NVCC="-DX=1 ..." builds lib/libpastar_gpu_<name>.so (load it with PASTAR_GPU_LIB)
+VARIANT = "phase" if PHASE else os.environ.get("PG_VARIANT", "")
+OBJ = os.path.join(HERE, "build_" + VARIANT if VARIANT else "build")
+LIB = os.path.join(HERE, "lib", "libpastar_gpu_%s.so" % VARIANT if VARIANT else "libpastar_gpu.so")
 BIN = os.path.join(HERE, "bin", "pastar")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
@@ -22,7 +24,7 @@ CXX = os.environ.get("CXX", "g++")
 CU_SOURCES = ["pg_api.cu", "pg_pairdp.cu", "pg_expand.cu", "pg_search.cu"]
 HOST_SOURCES = ["host/pg_host_weights.cpp"]
 CLI_SOURCES = ["host/pastar_main.cpp"]
-NVCC_FLAGS = (["-DPG_PHASE_TIMING"] if PHASE else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+NVCC_FLAGS = (["-DPG_PHASE_TIMING"] if PHASE else []) + os.environ.get("PG_EXTRA_NVCC", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 # -ffp-contract=off: the host weight routine must not fuse multiply-adds (float-order exact vs the reference)
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
@@ -76,7 +78,7 @@ def build(force=False, verbose=False, ptxas_info=False):
     if jobs or force or not os.path.exists(LIB):
         _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], verbose)
     cli = [os.path.join(CSRC, s) for s in CLI_SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    if cli and not PHASE and (force or _newer(cli + hdrs + [LIB], BIN)):
+    if cli and not VARIANT and (force or _newer(cli + hdrs + [LIB], BIN)):
         _run([CXX] + CXX_FLAGS + cli + ["-o", BIN, "-L" + os.path.dirname(LIB), "-lpastar_gpu", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"],
              verbose)
     return LIB

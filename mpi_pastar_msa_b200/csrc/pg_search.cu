@@ -889,8 +889,11 @@ __device__ __forceinline__ void ring_flush(const DevSearch &d, const unsigned lo
 
 // MODE 0: one partition.  MODE 1: successors owned by other partitions are sent to them as records.  MODE 2: they are
 // skipped - their owners generate them from the forwarded parent (claim_kernel<.., true>).
+#ifndef PG_EXPAND_CTAS
+#define PG_EXPAND_CTAS 3 // resident CTAs per SM the expand kernel is compiled for (register budget 65536 / 256 / this)
+#endif
 template <int N, int KEYW, int MODE>
-__global__ void __launch_bounds__(256, 3) expand_probe_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
+__global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
                                                               const __grid_constant__ OwnerArgs oa, const __grid_constant__ ParentSrc ps)
 {
     constexpr bool MULTI = MODE != 0;   // owners are computed
