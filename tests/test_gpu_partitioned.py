@@ -180,3 +180,11 @@ def test_multi_search_one_process(gpu_lib, name, parts, batch, ht, sh):
     assert tot["closed_size"] == sum(p["closed_size"] for p in per) > 0
     for G in Gs:
         G.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_p2p_modes_wide_key(gpu_lib, mode):
+    """The two-word key (KEYW = 2) through successor records (32-byte pg_xrec) and parent forwarding (24-byte parents)."""
+    from conftest import WIDE_CASES
+    r = p2p_search(gpu_lib, WIDE_CASES["fam10x100"], 4, 4096, "FZORDER", 6, mode, cap=1 << 24)
+    assert r["g"] == KNOWN_OPT["fam10x100"], r

@@ -41,6 +41,17 @@ def test_kinase_full(gpu_lib):
         assert weighted_sp_score(seqs, G.w_int, r["rows"]) == 421546
 
 
+def test_wide_key_search(gpu_lib):
+    """70 key bits: the KEYW = 2 instantiation of claim / expand+probe / insert / backtrace."""
+    from conftest import WIDE_CASES
+    seqs = WIDE_CASES["fam10x100"]
+    with gpu_lib.PastarGPU(seqs) as G:
+        G.build_pair_tables()
+        r = G.search(table_capacity=1 << 24, batch_target=4096)
+        assert r["finished"] == 1 and r["g"] == KNOWN_OPT["fam10x100"]
+        assert weighted_sp_score(seqs, G.w_int, r["rows"]) == r["g"]
+
+
 def test_budgeted_run_stops(gpu_lib):
     from conftest import random_seqs
     seqs = random_seqs(7, 400, 3)
