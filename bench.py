@@ -336,25 +336,32 @@ def run_ours(args, rank, world):
         extra["pair_dp"] = {"kernel": "pair_dp_kernel", "cells": cells, "ms": dp_ms, "gcups": cells / (dp_ms * 1e-3) / 1e9}
         del d_out
 
-        # ---- e2e: host buffers -> C ABI -> result.  The job is 2.5x the expansions of ramp-up + warm-up + timed region, so
+        # ---- e2e: host buffers -> C ABI -> result.  The job is 2x the expansions of ramp-up + warm-up + timed region, so
         # that the one-off set-up (context, 16 GiB table allocation and clear) does not dominate a sub-second search.
-        budget = int(2.5 * c1["expansions"])
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        G2 = m.PastarGPU(seqs, device=local)          # host weights + H2D of residues / cost table / weights
-        t_ctx = time.perf_counter() - t0
-        G2.build_pair_tables()
-        r = G2.search(table_capacity=cap, batch_target=batch, max_expansions=budget, want_rows=False)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        G2.close()
+        r, wall, t_ctx, factor = None, 0.0, 0.0, 2.0
+        while r is None:
+            budget = int(factor * c1["expansions"])
+            t0 = time.perf_counter()
+            G2 = m.PastarGPU(seqs, device=local)          # host weights + H2D of residues / cost table / weights
+            t_ctx = time.perf_counter() - t0
+            G2.build_pair_tables()
+            try:
+                r = G2.search(table_capacity=cap, batch_target=batch, max_expansions=budget, want_rows=False)
+            except m.PastarError:
+                if factor <= 1.0:
+                    raise
+                factor = 1.0                              # table / pool too small for the longer job: the timed arm's own length
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            G2.close()
         h2d = sum(((len(s) + 16) & ~15) for s in seqs) + 8100 * 4 + 2 * n + 16
         d2h = (r["rounds"] // 8 + 2) * 200 + 16
         line["e2e"] = {"value": r["expansions"] / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / max(1, r["rounds"]),
                        "d2h_bytes_per_step": d2h / max(1, r["rounds"]), "expansions": r["expansions"], "rounds": r["rounds"],
                        "wall_s": wall, "context_s": t_ctx, "search_kernel_s": r["kernel_ms"] * 1e-3,
                        "includes": "host Altschul weights, context create, pairwise DP, table allocation + clear, search from the start node "
-                                   "(2.5x the expansions of the timed arm's whole run), result read-back"}
+                                   "(%.1fx the expansions of the timed arm's whole run), result read-back" % factor}
         # ---- CPU baseline beside it (bounded sample)
         try:
             threads = os.cpu_count() or 1
@@ -366,7 +373,7 @@ def run_ours(args, rank, world):
         # ---- e2e at N GPUs: the whole job through the public multi-GPU API (mpi_pastar_msa_b200.dist over the C ABI) from
         # host buffers: per rank host weights, context create, pairwise DP, engine set-up (peer-mapped inboxes), the
         # search from the start node budgeted to the expansions the timed arm did in total, status read-backs.
-        budget = int(2.5 * tot1[0])
+        budget = int(tot1[0])
         G.close()
         torch.cuda.synchronize()
         dist.barrier()

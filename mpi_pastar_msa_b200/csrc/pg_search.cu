@@ -1982,7 +1982,7 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     PG_CUDA(ctx, cudaGetLastError());
     // Every table slot is pushed once per improvement.  Chunk sizes double, so a bucket wastes at most its own
     // size; each non-empty bucket holds at least one unit.
-    uint64_t units = 3 * (cap / UNIT) + (uint64_t)s->f_range + 4096;
+    uint64_t units = 5 * (cap / UNIT) + (uint64_t)s->f_range + 4096; // measured: 2.7 pushes per table entry + chunk slack
     s->n_units = (uint32_t)std::min<uint64_t>(units, 0x7ffffff0ull);
     PG_CUDA(ctx, cudaMalloc(&s->d_pool, (size_t)s->n_units * UNIT * 4));
     PG_CUDA(ctx, cudaMalloc(&s->d_link, (size_t)s->n_units * 8));
