@@ -235,6 +235,7 @@ struct DevSearch {
     char *peer_inbox[16];
     unsigned long long *peer_counts[16];
     int p2p;
+    int f0, f_range;              // bucket 0 is f == f0; number of buckets
     unsigned long long *live;     // compacted live parents of the round, word-major: live[w * live_cap + i]
     unsigned long long live_cap;
     unsigned long long *surv;     // local survivors of the round
@@ -348,11 +349,10 @@ __device__ __noinline__ void bucket_place_slow(const DevSearch &d, int b, uint32
 // bucket index of f, or -1 (error raised) when f is beyond the bucket range
 __device__ __forceinline__ int bucket_of(const DevSearch &d, int f)
 {
-    SearchCtrl *c = d.ctrl;
-    int b = f - c->f0;
-    if (b < 0) b = 0; // cannot happen with a consistent heuristic; keep it poppable
-    if (b >= c->f_range) {
-        c->error = 3;
+    int b = f - d.f0; // f0 / f_range are constants of the search: read from the kernel parameters, not from the control
+    if (b < 0) b = 0; // block whose line is busy with counter atomics; b < 0 cannot happen with a consistent heuristic
+    if (b >= d.f_range) {
+        d.ctrl->error = 3;
         return -1;
     }
     return b;
@@ -1247,7 +1247,7 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
         cn.inserted += fl & UPS_INSERTED;
         cn.pushed += (fl >> 1) & 1u;
         cn.reopen += (fl >> 2) & 1u;
-        if (fl & UPS_PUSHED) min_b = min(min_b, (int)(unsigned)g_f - c->f0);
+        if (fl & UPS_PUSHED) min_b = min(min_b, (int)(unsigned)g_f - d.f0);
     };
     const long long stride = (long long)gridDim.x * blockDim.x;
     // the trip count is warp-uniform: the deferred ring is a warp-level structure
@@ -1626,6 +1626,8 @@ DevSearch dev_search(const pg_ctx *ctx)
         d.peer_counts[i] = s->peer_counts[i] ? s->peer_counts[i] + (size_t)s->p2p_buf * s->cfg.n_parts : nullptr;
     }
     d.live = s->d_live;
+    d.f0 = s->f0;
+    d.f_range = s->f_range;
     d.live_cap = s->live_cap;
     d.surv = s->d_surv;
     d.surv_cap = s->surv_cap;
