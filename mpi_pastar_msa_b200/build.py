@@ -76,7 +76,7 @@ def build(force=False, verbose=False, ptxas_info=False):
     with ThreadPoolExecutor(max_workers=max(1, min(8, len(jobs)))) as ex:
         list(ex.map(lambda c: _run(c, verbose or ptxas_info), jobs))
     if jobs or force or not os.path.exists(LIB):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], verbose)
+        _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lpthread"], verbose)
     cli = [os.path.join(CSRC, s) for s in CLI_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if cli and not VARIANT and (force or _newer(cli + hdrs + [LIB], BIN)):
         _run([CXX] + CXX_FLAGS + cli + ["-o", BIN, "-L" + os.path.dirname(LIB), "-lpastar_gpu", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"],

@@ -17,6 +17,10 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "pastar_gpu.h"
@@ -290,9 +294,29 @@ extern "C" int pg_host_weights(int n_seq, const char *const *seqs, const int *le
         if (!seqs[i] || lens[i] < 1) return PG_ERR_ARG;
         s[i] = "-" + std::string(seqs[i], seqs[i] + lens[i]); // WeightedSP.cpp:447
     }
+    // The N(N-1)/2 pair distances (the reference's `primer`, WeightedSP.cpp:144-244) are independent of each other:
+    // computed on as many host threads as there are pairs / cores.  Each pair runs the same float operations in the
+    // same order as the serial loop, so the result is bit-identical.
     std::vector<float> dist((size_t)n * n, 0.0f);
-    for (int i = 0; i < n - 1; i++)
-        for (int j = i + 1; j < n; j++) dist[(size_t)i * n + j] = dist[(size_t)j * n + i] = pair_distance(s[i], s[j]);
+    {
+        std::vector<std::pair<int, int>> todo;
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n; j++) todo.emplace_back(i, j);
+        std::atomic<size_t> next(0);
+        auto work = [&]() {
+            for (size_t k = next.fetch_add(1); k < todo.size(); k = next.fetch_add(1)) {
+                const int i = todo[k].first, j = todo[k].second;
+                dist[(size_t)i * n + j] = dist[(size_t)j * n + i] = pair_distance(s[i], s[j]);
+            }
+        };
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt == 0) nt = 1;
+        nt = (unsigned)std::min<size_t>(nt, todo.size());
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (std::thread &t : pool) t.join();
+    }
 
     NJ nj(dist, n);
     nj.build();
