@@ -333,7 +333,47 @@ def run_ours(args, rank, world):
                                         "frac": probes / gl}
         except Exception as ex:
             extra["gather_roofline"] = {"error": repr(ex)}
-        extra["pair_dp"] = {"kernel": "pair_dp_kernel", "cells": cells, "ms": dp_ms, "gcups": cells / (dp_ms * 1e-3) / 1e9}
+        # integer peak for the DP: 148 SMs x 128 lanes x SM clock, at the 26 thread instructions per cell the kernel executes
+        int_peak_gcups = 148 * 128 * (clocks.get("sm_mhz") or 1965) * 1e6 / 26 / 1e9
+        extra["pair_dp"] = {"kernel": "pair_dp_kernel", "cells": cells, "ms": dp_ms, "gcups": cells / (dp_ms * 1e-3) / 1e9,
+                            "frac_of_integer_peak": cells / (dp_ms * 1e-3) / 1e9 / int_peak_gcups,
+                            "integer_peak_gcups": int_peak_gcups, "note": "one CTA per pair: 21 of 148 SMs busy"}
+        # ---- BASELINE configs[4]: synthetic 8 x 1000 - the 28-table heuristic build and the batched expansion at N = 8
+        try:
+            import random
+            r8 = random.Random(SEED)
+            seqs8 = ["".join(r8.choice(AA) for _ in range(1000)) for _ in range(8)]
+            G8 = m.PastarGPU(seqs8, device=local)
+            G8.set_stream(stream.cuda_stream)
+            dp8 = min(G8.build_pair_tables() for _ in range(3))
+            cells8 = sum((len(a) + 1) * (len(b) + 1) for i, a in enumerate(seqs8) for b in seqs8[i + 1:])
+            K8 = 50000
+            pos8 = np.stack([rng.integers(0, 1000, K8) for _ in range(8)], axis=1).astype(np.uint16)
+            nodes8 = G8.make_nodes(pos8, rng.integers(0, 100000, K8), rng.integers(1, 256, K8))
+            d_par8 = torch.from_numpy(nodes8.view(np.uint8).reshape(K8, -1)).cuda()
+            sst8 = m.succ_dtype(8).itemsize
+            d_out8 = torch.empty(K8 * 255 * sst8, dtype=torch.uint8, device="cuda")
+            d_cnt8 = torch.empty(K8, dtype=torch.int32, device="cuda")
+            for _ in range(3):
+                G8.expand_batch_dev(d_par8.data_ptr(), K8, 8, d_out8.data_ptr(), d_cnt8.data_ptr(), st)
+            torch.cuda.synchronize()
+            a0.record(stream)
+            for _ in range(10):
+                G8.expand_batch_dev(d_par8.data_ptr(), K8, 8, d_out8.data_ptr(), d_cnt8.data_ptr(), st)
+            a1.record(stream)
+            torch.cuda.synchronize()
+            x8 = a0.elapsed_time(a1) / 10
+            b8 = m.node_dtype(8).itemsize + 8 + 16 * 28 + 255 * sst8  # 8644 B at N=8
+            extra["s8"] = {"workload": "synthetic N=8 x L=1000 (seed %d)" % SEED,
+                           "pair_dp": {"tables": 28, "cells": cells8, "ms": dp8, "gcups": cells8 / (dp8 * 1e-3) / 1e9,
+                                       "frac_of_integer_peak": cells8 / (dp8 * 1e-3) / 1e9 / int_peak_gcups},
+                           "expand_only": {"kernel": "expand_batch_kernel<8>", "expansions_per_sec": K8 / (x8 * 1e-3),
+                                           "successors_per_sec": K8 * 255 / (x8 * 1e-3), "bytes_per_expansion": b8,
+                                           "achieved_gbs": K8 * b8 / (x8 * 1e-3) / 1e9, "frac_of_hbm": K8 * b8 / (x8 * 1e-3) / 1e9 / hbm}}
+            del d_out8
+            G8.close()
+        except Exception as ex:
+            extra["s8"] = {"error": repr(ex)}
         del d_out
 
         # ---- e2e: host buffers -> C ABI -> result.  The job is 2x the expansions of ramp-up + warm-up + timed region, so
