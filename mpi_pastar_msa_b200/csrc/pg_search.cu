@@ -30,7 +30,9 @@
 #include <chrono>
 #include <climits>
 #include <cstdio>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "pg_expand_core.cuh"
@@ -2435,60 +2437,139 @@ extern "C" int pg_multi_search(pg_ctx *const *ctxs, int n_gpus, const pg_search_
             cudaGetLastError();
         }
     }
-    for (int i = 0; i < G; i++) {
-        pg_search_config ci = cfg;
-        ci.n_parts = G;
-        ci.part = i;
-        ci.reserved = 2; // parent forwarding
-        MG_CHECK(i, pg_search_begin(ctxs[i], &ci));
-        MG_CUDA(i, cudaSetDevice(ctxs[i]->device));
-        const size_t bytes = 2 * (size_t)G * ctxs[i]->search->region_bytes;
-        MG_CUDA(i, cudaMalloc(&inbox[i], bytes));
-        MG_CUDA(i, cudaMalloc(&counts[i], 2 * (size_t)G * 8));
-        MG_CUDA(i, cudaMemset(counts[i], 0, 2 * (size_t)G * 8));
-        MG_CUDA(i, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    {   // search state, inbox and count array of every device, set up concurrently (tens of GB to allocate and clear each)
+        std::vector<int> brc(G, PG_OK);
+        auto begin_one = [&](int i) {
+            pg_search_config ci = cfg;
+            ci.n_parts = G;
+            ci.part = i;
+            ci.reserved = 2; // parent forwarding
+            if ((brc[i] = pg_search_begin(ctxs[i], &ci)) != PG_OK) return;
+            const size_t bytes = 2 * (size_t)G * ctxs[i]->search->region_bytes;
+            cudaError_t e = cudaSetDevice(ctxs[i]->device);
+            if (e == cudaSuccess) e = cudaMalloc(&inbox[i], bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&counts[i], 2 * (size_t)G * 8);
+            if (e == cudaSuccess) e = cudaMemset(counts[i], 0, 2 * (size_t)G * 8);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) brc[i] = pg_fail(ctxs[i], PG_ERR_CUDA, std::string("pg_multi_search set-up: ") + cudaGetErrorString(e));
+        };
+        std::vector<std::thread> th;
+        for (int i = 1; i < G; i++) th.emplace_back(begin_one, i);
+        begin_one(0);
+        for (std::thread &t : th) t.join();
+        for (int i = 0; i < G; i++) MG_CHECK(i, brc[i]);
     }
     for (int i = 0; i < G; i++) {
         MG_CHECK(i, pg_search_set_peers(ctxs[i], inbox.data(), G));
         MG_CHECK(i, pg_search_set_peer_counts(ctxs[i], counts.data(), G, 2));
     }
 
-    // ---- rounds
+    // ---- rounds.  One host thread per device runs that device's whole loop (the reference: one worker thread per
+    // partition, PAStar.cpp:650-651).  Inside a round a thread only waits, spinning on a host flag, until its peers have
+    // RECORDED this round's "forwarded" event - the wait for the event itself happens on the GPU stream - and the
+    // threads meet at a host barrier for the stop test every few rounds.
     const int per_sync = cfg.rounds_per_sync > 0 ? cfg.rounds_per_sync : 4;
     int best = INT_MAX, min_open = INT_MAX;
     bool finished = false;
     std::vector<pg_result> pr(G);
-    for (;;) {
-        for (int r = 0; r < per_sync; r++) {
-            for (int i = 0; i < G; i++) MG_CHECK(i, pg_search_round_async(ctxs[i], best));
-            // barrier: nobody reads its inbox before every partition's forward + publish kernels of this round are done
-            for (int i = 0; i < G; i++) {
-                MG_CUDA(i, cudaSetDevice(ctxs[i]->device));
-                MG_CUDA(i, cudaEventRecord(ev[i], ctxs[i]->stream));
+    std::vector<cudaEvent_t> ev2(G, nullptr); // second event per device: rounds alternate, so a peer one round ahead does not re-record the one being waited for
+    for (int i = 0; i < G; i++) {
+        MG_CUDA(i, cudaSetDevice(ctxs[i]->device));
+        MG_CUDA(i, cudaEventCreateWithFlags(&ev2[i], cudaEventDisableTiming));
+    }
+    {
+        std::atomic<int> fail(-1), arrive(0), gsense(0), stop(0);
+        std::vector<std::atomic<long>> recorded(G);
+        for (auto &r : recorded) r.store(-1);
+        std::vector<int> fail_rc(G, PG_OK);
+        std::vector<int32_t> mn_v(G, INT_MAX), bg_v(G, INT_MAX);
+        int shared_best = INT_MAX;
+        auto failed = [&]() { return fail.load(std::memory_order_acquire) >= 0; };
+        auto relax = [](unsigned &n) {
+            if (++n & 1023u) return;
+            std::this_thread::yield();
+        };
+        auto barrier = [&](int &sense) -> bool { // sense-reversing; gives up when a peer has failed
+            sense ^= 1;
+            if (arrive.fetch_add(1, std::memory_order_acq_rel) + 1 == G) {
+                arrive.store(0, std::memory_order_relaxed);
+                gsense.store(sense, std::memory_order_release);
+            } else {
+                unsigned n = 0;
+                while (gsense.load(std::memory_order_acquire) != sense && !failed()) relax(n);
             }
-            for (int j = 0; j < G; j++) {
-                MG_CUDA(j, cudaSetDevice(ctxs[j]->device));
-                for (int i = 0; i < G; i++)
-                    if (i != j) MG_CUDA(j, cudaStreamWaitEvent(ctxs[j]->stream, ev[i], 0));
+            return !failed();
+        };
+        auto worker = [&](int i) {
+            auto bail = [&](int e) {
+                fail_rc[i] = e;
+                int expect = -1;
+                fail.compare_exchange_strong(expect, i);
+            };
+            int sense = 0, my_best = INT_MAX;
+            long round = 0;
+            for (;;) {
+                for (int r = 0; r < per_sync; r++, round++) {
+                    int e = pg_search_round_async(ctxs[i], my_best); // parents and counts are on their way when the event fires
+                    if (e != PG_OK) return bail(e);
+                    cudaEvent_t mine = (round & 1) ? ev2[i] : ev[i];
+                    if (cudaEventRecord(mine, ctxs[i]->stream) != cudaSuccess) return bail(pg_fail(ctxs[i], PG_ERR_CUDA, "cudaEventRecord failed"));
+                    recorded[i].store(round, std::memory_order_release);
+                    for (int q = 0; q < G; q++) { // barrier on the stream: nobody reads its inbox before every partition has forwarded
+                        if (q == i) continue;
+                        unsigned n = 0;
+                        while (recorded[q].load(std::memory_order_acquire) < round && !failed()) relax(n);
+                        if (failed()) return;
+                        if (cudaStreamWaitEvent(ctxs[i]->stream, (round & 1) ? ev2[q] : ev[q], 0) != cudaSuccess)
+                            return bail(pg_fail(ctxs[i], PG_ERR_CUDA, "cudaStreamWaitEvent failed"));
+                    }
+                    if ((e = pg_search_insert_inbox_async(ctxs[i])) != PG_OK) return bail(e);
+                }
+                // stop test (PAStar.cpp:410-547): nothing is in flight once every stream has drained
+                int e = pg_search_sync(ctxs[i]);
+                if (e == PG_OK) e = pg_search_status(ctxs[i], &mn_v[i], &bg_v[i], &pr[i]);
+                if (e != PG_OK) return bail(e);
+                if (!barrier(sense)) return;
+                if (i == 0) {
+                    int mo = INT_MAX, bs = shared_best;
+                    int64_t expansions = 0;
+                    for (int q = 0; q < G; q++) {
+                        mo = std::min(mo, (int)mn_v[q]);
+                        bs = std::min(bs, (int)bg_v[q]);
+                        expansions += pr[q].expansions;
+                    }
+                    shared_best = bs;
+                    min_open = mo;
+                    if (mo >= bs || mo == INT_MAX) {
+                        finished = bs != INT_MAX;
+                        stop.store(1);
+                    } else if (cfg.max_expansions > 0 && expansions >= cfg.max_expansions) {
+                        stop.store(1);
+                    }
+                }
+                if (!barrier(sense)) return;
+                my_best = shared_best;
+                if (stop.load()) return;
             }
-            for (int i = 0; i < G; i++) MG_CHECK(i, pg_search_insert_inbox_async(ctxs[i]));
-        }
-        // stop test (PAStar.cpp:410-547): nothing is in flight once every stream has drained
-        for (int i = 0; i < G; i++) MG_CHECK(i, pg_search_sync(ctxs[i]));
-        min_open = INT_MAX;
-        int64_t expansions = 0;
+        };
+        const auto tr0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int i = 1; i < G; i++) th.emplace_back(worker, i);
+        worker(0);
+        for (std::thread &t : th) t.join();
+        total->kernel_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
+        best = shared_best;
+        const int bad = fail.load();
         for (int i = 0; i < G; i++) {
-            int32_t mn = 0, bg = 0;
-            MG_CHECK(i, pg_search_status(ctxs[i], &mn, &bg, &pr[i]));
-            min_open = std::min(min_open, (int)mn);
-            best = std::min(best, (int)bg);
-            expansions += pr[i].expansions;
+            cudaSetDevice(ctxs[i]->device);
+            if (ev2[i]) cudaEventDestroy(ev2[i]);
         }
-        if (min_open >= best || min_open == INT_MAX) {
-            finished = best != INT_MAX;
-            break;
+        if (bad >= 0) {
+            rc = fail_rc[bad];
+            if (ctxs[bad] != c0) c0->err = ctxs[bad]->err;
+            cleanup();
+            return rc;
         }
-        if (cfg.max_expansions > 0 && expansions >= cfg.max_expansions) break;
     }
 
     // ---- results: counters per partition and summed; open / closed census (PAStar.cpp:591-619)
@@ -2551,7 +2632,6 @@ extern "C" int pg_multi_search(pg_ctx *const *ctxs, int n_gpus, const pg_search_
     cleanup();
     for (int i = 0; i < G; i++) pg_search_end(ctxs[i]);
     total->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    total->kernel_ms = total->seconds * 1e3;
     return PG_OK;
 #undef MG_CHECK
 #undef MG_CUDA
