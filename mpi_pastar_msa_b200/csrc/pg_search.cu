@@ -93,6 +93,7 @@ struct SearchState {
     int p2p_nbuf = 1, p2p_buf = 0;                   // double-buffered inboxes: one cross-GPU barrier per round is enough
     bool p2p = false;
     bool forward = false;      // P2P parent forwarding (pg_search_config.reserved == 2)
+    bool merge_expand = false; // forwarding: own and forwarded parents expanded by ONE launch after the barrier
     size_t region_bytes = 0;   // bytes one source may write into one inbox (per buffer)
     int xrec = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -634,7 +635,8 @@ struct ParentSrc {
     const unsigned long long *base[16];
     const unsigned long long *count[16];
     unsigned long long cap;
-    int n, own;
+    int n;
+    unsigned own; // bit r: region r holds this partition's own parents
 };
 
 // Partitions (bit set) that own at least one successor of the node `key`; `part` itself is not reported.
@@ -997,7 +999,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
             } else {
                 // the goal is reached from here by moving every sequence that is one short of its end
                 goal_mask = alive == onestep ? alive : 0;
-                if (sub == 0 && ps.own) n_exp++;
+                if (sub == 0 && ((ps.own >> rg) & 1u)) n_exp++;
                 pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
             }
         }
@@ -1685,14 +1687,14 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
     const DevSearch d = dev_search(ctx);
     ParentSrc ps;
     memset(&ps, 0, sizeof(ps));
-    if (!inbox) {
-        ps.n = 1;
-        ps.own = 1;
-        ps.cap = s->live_cap;
-        ps.base[0] = s->d_live;
-        ps.count[0] = &s->d_ctrl->live_n;
-    } else {
-        ps.own = 0;
+    ps.cap = s->live_cap; // == outbox_cap in forwarding mode: the regions of one launch share a layout
+    if (!inbox || s->merge_expand) { // this partition's own live parents
+        ps.base[ps.n] = s->d_live;
+        ps.count[ps.n] = &s->d_ctrl->live_n;
+        ps.own |= 1u << ps.n;
+        ps.n++;
+    }
+    if (inbox) { // the parents the other partitions forwarded
         ps.cap = s->outbox_cap;
         for (int src = 0; src < s->cfg.n_parts; src++) {
             if (src == s->cfg.part) continue;
@@ -1823,8 +1825,10 @@ int launch_round(pg_ctx *ctx, int f_limit)
         }
     }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
-    rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
-    if (rc != PG_OK) return rc;
+    if (!s->merge_expand) {
+        rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
+        if (rc != PG_OK) return rc;
+    }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     if (!s->forward) { // forwarding: the survivors are inserted after the forwarded parents have been expanded as well
         if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
@@ -2014,6 +2018,7 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     }
     if (cfg->n_parts > 1) {
         s->forward = cfg->reserved == 2;
+        s->merge_expand = s->forward && getenv("PG_MERGE_EXPAND") && atoi(getenv("PG_MERGE_EXPAND")) != 0;
         if (s->forward) {
             // parent forwarding: a destination receives at most every live parent of the round
             s->outbox_cap = (uint64_t)s->batch_target + UNIT;
