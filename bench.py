@@ -10,8 +10,10 @@ A step = one search round of the hot path: pop `batch` frontier nodes -> expand 
 (g via weighted SP, h via pairwise tables, owner) -> closed/open-table dedupe -> push survivors (+ exchange for N>1).
 value  = expansions in the K timed steps / device time (state resident in HBM), whole job over all ranks.
 e2e    = same metric through the C ABI from HOST buffers: context create (H2D of sequences, cost, weights), pairwise
-         tables, search to the same expansion budget, result D2H; wall clock around the calls.
-roofline = the fused expand+dedupe kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+         tables, table allocation, search from the start node to an expansion budget, result D2H; wall clock around the
+         calls (N > 1: the same through mpi_pastar_msa_b200.dist, per-rank set-up included).
+roofline = the round's dominant kernel (expand + probe) against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+         roofline.kernels lists select / claim / expand+probe / insert with their CUDA-event times and algorithmic bytes.
 cpu_baseline / --impl reference = the reference's own getNeigh / PairAlign / weights (oracle/_ref, compiled from
          the unmodified sources) under the restated T-thread hash-partitioned driver, on this box's host cores.
 """
