@@ -2280,13 +2280,52 @@ extern "C" int pg_search(pg_ctx *ctx, const pg_search_config *cfg_in, pg_result 
     SearchState *s = ctx->search;
     const int per_sync = cfg.rounds_per_sync > 0 ? cfg.rounds_per_sync : 8;
     PG_CUDA(ctx, cudaEventRecord(s->ev0, ctx->stream));
-    for (;;) {
-        for (int r = 0; r < per_sync; r++)
-            if ((rc = launch_round(ctx, INT_MAX)) != PG_OK) return rc;
-        if ((rc = sync_ctrl(ctx)) != PG_OK) return rc;
+    // Every round is the same four launches with the same arguments (all per-round state lives in the device control
+    // block), so after a first, ordinary group of rounds the group is captured once into a CUDA graph and replayed: small
+    // inputs (kinase.fasta: ~10 us of kernel time per round) are bound by launch overhead, not by the kernels.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    bool try_graph = !s->profile && !getenv("PG_NO_GRAPH");
+    for (long group = 0;; group++) {
+        if (gexec) {
+            PG_CUDA(ctx, cudaGraphLaunch(gexec, ctx->stream));
+            s->rounds += per_sync;
+        } else {
+            const bool capture = try_graph && group == 1;
+            if (capture && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                try_graph = false;
+            }
+            const bool capturing = capture && try_graph;
+            for (int r = 0; r < per_sync; r++)
+                if ((rc = launch_round(ctx, INT_MAX)) != PG_OK) {
+                    if (capturing) {
+                        cudaStreamEndCapture(ctx->stream, &graph);
+                        if (graph) cudaGraphDestroy(graph);
+                    }
+                    return rc;
+                }
+            if (capturing) {
+                if (cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess) {
+                    PG_CUDA(ctx, cudaGraphLaunch(gexec, ctx->stream)); // the captured rounds have not run yet
+                } else { // no graph on this driver: run the group the ordinary way from now on
+                    cudaGetLastError();
+                    gexec = nullptr;
+                    try_graph = false;
+                    s->rounds -= per_sync;
+                    for (int r = 0; r < per_sync; r++)
+                        if ((rc = launch_round(ctx, INT_MAX)) != PG_OK) return rc;
+                }
+            }
+        }
+        if ((rc = sync_ctrl(ctx)) != PG_OK) break;
         if (s->h_ctrl->done) break;
         if (cfg.max_expansions > 0 && (int64_t)s->h_ctrl->expansions >= cfg.max_expansions) break;
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != PG_OK) return rc;
     PG_CUDA(ctx, cudaEventRecord(s->ev1, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
