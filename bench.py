@@ -217,7 +217,12 @@ def run_ours(args, rank, world):
             eng = CudaEngine(G, world, rank, cap, batch)
             extra["exchange"] = "nccl all_to_all_single (p2p unavailable: %r)" % (ex,)
         drv = PartitionedSearch(eng, dist, seqs, lambda pos: int(G.owner(np.array(pos, dtype=np.uint16), world)[0]))
-        launches_per_step = 5 + (world - 1)  # select, claim, expand/probe, insert (local), publish counts + one insert per source
+        if isinstance(eng, CudaEngineP2P) and eng.forward:
+            launches_per_step = 7  # select, claim, forward, publish counts, expand (own), expand (forwarded), insert
+        elif isinstance(eng, CudaEngineP2P):
+            launches_per_step = 5 + (world - 1)  # select, claim, expand/probe, insert (local), publish counts + one insert per source
+        else:
+            launches_per_step = 6  # select, claim, expand/probe, insert (local), insert (received), status select
         chained = getattr(eng, "async_rounds", False)  # device-driven rounds: one status exchange per call, not per round
         ramp = 0
         while True:
