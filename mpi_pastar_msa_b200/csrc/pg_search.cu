@@ -124,12 +124,15 @@ struct Key<1> {
     __device__ __forceinline__ void add_val(unsigned v, int off) { lo += (unsigned long long)v << off; }
     __device__ __forceinline__ Key plus(const Key &o) const { return Key{lo + o.lo}; }
     __device__ __forceinline__ unsigned field(int off, unsigned m) const { return (unsigned)(lo >> off) & m; }
+    // 32-bit mix of the two key halves (the table has at most 2^32 slots): 3 multiplies instead of two 64-bit ones
     __device__ __forceinline__ unsigned long long hash() const
     {
-        unsigned long long h = lo * 0x9E3779B97F4A7C15ull;
-        h ^= h >> 32;
-        h *= 0xD6E8FEB86659FD93ull;
-        h ^= h >> 29;
+        unsigned h = (unsigned)lo * 0x9E3779B1u + (unsigned)(lo >> 32) * 0x85EBCA77u;
+        h ^= h >> 15;
+        h *= 0xC2B2AE3Du;
+        h ^= h >> 13;
+        h *= 0x27D4EB2Fu;
+        h ^= h >> 16;
         return h;
     }
 };
@@ -157,10 +160,13 @@ struct Key<2> {
     }
     __device__ __forceinline__ unsigned long long hash() const
     {
-        unsigned long long h = (lo ^ (hi * 0xC2B2AE3D27D4EB4Full)) * 0x9E3779B97F4A7C15ull;
-        h ^= h >> 32;
-        h *= 0xD6E8FEB86659FD93ull;
-        h ^= h >> 29;
+        unsigned h = (unsigned)lo * 0x9E3779B1u + (unsigned)(lo >> 32) * 0x85EBCA77u + (unsigned)hi * 0x165667B1u +
+                     (unsigned)(hi >> 32) * 0xD3A2646Cu;
+        h ^= h >> 15;
+        h *= 0xC2B2AE3Du;
+        h ^= h >> 13;
+        h *= 0x27D4EB2Fu;
+        h ^= h >> 16;
         return h;
     }
 };
