@@ -1,31 +1,34 @@
-// Kernels 3+ — the batched PA-Star search: per-GPU closed/open hash table,
-// f-indexed open buckets, batched pop, fused expand + owner + dedupe + push.
+// Kernels 3+ — the batched PA-Star search: per-GPU closed/open hash table, f-indexed open buckets, and the round
+// select -> claim -> expand + probe -> insert (+ the multi-GPU exchange modes and the one-process multi-GPU driver).
 //
 // Replaces, for one hash-owned partition (reference: one worker thread):
 //   PAStar<N>::worker_inner      pastar/PAStar.cpp:319-401   pop / closed check / expand / reconcile
 //   PAStar<N>::enqueue           pastar/PAStar.cpp:219-237   closed-list dedupe + reopen
 //   PriorityList<N>              pastar/include/PriorityList.h:84-122  (pos-unique, min-f pop)
 //   process_final_node/check_stop pastar/PAStar.cpp:410-547  optimality-preserving stop
+//   sender / receiver / decoder  pastar/pastar_functions/*.cpp          successor exchange between partitions
 //
 // Data layout in HBM (all device resident, nothing per-node on the host):
 //   table   open-addressing hash table, one entry per coordinate ever generated:
-//             KEYW=1: {u64 key+1, u64 val}            16 B (two per 32 B sector)
-//             KEYW=2: {u64 key.lo+1.., u64 key.hi, u64 val, pad} 32 B
+//             KEYW=1: {u64 key+1, u64 val}            16 B (eight per 128 B line)
+//             KEYW=2: {u64 key.lo, u64 key.hi|1<<63, u64 val, pad} 32 B
 //           key = coordinates packed key_bits each; val = ~(g<<32 | open<<31 | parenti)
 //           so a zeroed table is empty and "no g yet".  This is ClosedList and the
-//           pos-index of OpenList in one structure: best g per coordinate.
+//           pos-index of OpenList in one structure: best g per coordinate.  The placement
+//           (home_slot) keeps the successors of one parent in shared 128-byte lines.
 //   buckets one u64 per f value {chunk offset, log2 size, fill}: the priority index of
 //           OpenList.  A bucket is a backward-linked list of chunks of u32 table slots
 //           whose sizes double (64, 128, ... 256 Ki entries), so a bucket of any size
 //           is a handful of contiguous runs; push = one atomicAdd, pop = whole chunks.
-//   plan    per round: the chunks selected by the select kernel.
-// A round is two launches on one stream: select (1 CTA) then expand (persistent
-// grid).  The host only reads the 128-byte control block every few rounds.
+//   plan / live / surv   per round: chunks selected by the select kernel, parents that
+//           survived the closed-bit claim, successors that passed the read-only probe.
+// A round is four launches on one stream (select, claim, expand + probe, insert); every count
+// that links them lives in the device control block, which the host reads every few rounds.
 //
-// Duplicate detection (the dominant cost): one 16 B load per successor; 90+ % of
-// successors are rejected right there (same key, g not better) without any
-// atomic or write.  New keys take one CAS on the key word; improvements one CAS
-// on the value word; only those are pushed to the open buckets.
+// Duplicate detection (the dominant cost): one 16 B load per successor in the expand kernel;
+// 88 % of successors are rejected right there (same key, g not better) without any atomic or
+// write.  The rest goes through the insert kernel: new keys take one CAS on the key word,
+// improvements one CAS on the value word; only those are pushed to the open buckets.
 #include <algorithm>
 #include <chrono>
 #include <climits>
