@@ -148,3 +148,64 @@ def test_partitioned_search_two_ranks(name, batch):
     assert got[0]["expansions"] == got[1]["expansions"] >= 1   # allreduced totals agree on every rank
     assert got[0]["bytes_sent"] + got[1]["bytes_sent"] > 0      # successors really crossed partitions
     assert got[0]["table"] > 0 and got[1]["table"] > 0          # both partitions own part of the state space
+
+
+class ChainedOracleEngine(OracleEngine):
+    """Stand-in for CudaEngineP2P: the engine itself moves the records (here: a gloo all-to-all) and the driver chains
+    several rounds between status exchanges, passing a best-goal bound that is a few rounds old."""
+
+    async_rounds = True
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.bytes_sent = 0
+
+    def round_and_exchange(self, f_limit, d):
+        out = self.round(f_limit)
+        send_n = torch.tensor([b.numel() for b in out], dtype=torch.int64)
+        recv_n = torch.empty_like(send_n)
+        d.all_to_all_single(recv_n, send_n)
+        inbox = torch.empty(int(recv_n.sum()), dtype=torch.uint8)
+        d.all_to_all_single(inbox, torch.cat(out) if int(send_n.sum()) else torch.empty(0, dtype=torch.uint8),
+                            output_split_sizes=recv_n.tolist(), input_split_sizes=send_n.tolist())
+        self.bytes_sent += int(send_n.sum())
+        self.insert(inbox)
+
+
+def _worker_chained(rank, world, port, name, batch, per_status, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mpi_pastar_msa_b200.dist import PartitionedSearch
+    from oracle import oracle as O
+    seqs = CASES[name]
+    eng = ChainedOracleEngine(seqs, world, rank, batch)
+    drv = PartitionedSearch(eng, dist, seqs, lambda pos: O.owner(pos, eng.ht, eng.sh, world))
+    drv.rounds_per_status = per_status
+    res = drv.run()
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,batch,per_status", [("PF08184", 4, 4), ("fam5x60", 32, 3), ("test2", 8, 8)])
+def test_chained_rounds_keep_the_optimum(name, batch, per_status):
+    """Device-driven engines run `rounds_per_status` rounds between stop tests with a stale best-goal bound: the rounds
+    past the optimum only pop nodes with f >= g*, so the result must not change."""
+    from oracle import oracle as O
+    seqs = CASES[name]
+    ref = O.Problem(seqs).astar(want_rows=False)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_chained, args=(r, 2, port, name, batch, per_status, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert got[r]["finished"] == 1 and got[r]["g"] == ref["g"], (name, r, got[r]["g"], ref["g"])
+        assert got[r]["rounds"] % per_status == 0
+        assert weighted_sp_score(seqs, O.Problem(seqs).int_weights(), got[r]["rows"]) == ref["g"]
