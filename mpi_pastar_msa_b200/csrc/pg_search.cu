@@ -387,16 +387,47 @@ __device__ __forceinline__ void bucket_push(const DevSearch &d, int f, uint32_t 
 // ---------------------------------------------------------------------------------------------
 // select: pick the chunks to pop this round (one CTA)
 // ---------------------------------------------------------------------------------------------
+// Inclusive scan of a[] and b2[] over the SELECT_THREADS (= 32 warps x 32) threads of the CTA, in place: shuffles inside
+// a warp, the 32 warp totals scanned by warp 0, three barriers in all.
 __device__ __forceinline__ void block_scan2(unsigned *a, unsigned *b2, int t)
 {
-    for (int off = 1; off < SELECT_THREADS; off <<= 1) {
-        const unsigned v = t >= off ? a[t - off] : 0;
-        const unsigned v2 = t >= off ? b2[t - off] : 0;
-        __syncthreads();
-        a[t] += v;
-        b2[t] += v2;
-        __syncthreads();
+    __shared__ unsigned s_wa[32], s_wb[32];
+    const int lane = t & 31, w = t >> 5;
+    unsigned x = a[t], y = b2[t];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned vx = __shfl_up_sync(0xffffffffu, x, off), vy = __shfl_up_sync(0xffffffffu, y, off);
+        if (lane >= off) {
+            x += vx;
+            y += vy;
+        }
     }
+    if (lane == 31) {
+        s_wa[w] = x;
+        s_wb[w] = y;
+    }
+    __syncthreads();
+    if (w == 0) {
+        unsigned tx = s_wa[lane], ty = s_wb[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned vx = __shfl_up_sync(0xffffffffu, tx, off), vy = __shfl_up_sync(0xffffffffu, ty, off);
+            if (lane >= off) {
+                tx += vx;
+                ty += vy;
+            }
+        }
+        s_wa[lane] = tx;
+        s_wb[lane] = ty;
+    }
+    __syncthreads();
+    if (w > 0) {
+        x += s_wa[w - 1];
+        y += s_wb[w - 1];
+    }
+    a[t] = x;
+    b2[t] = y;
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, long long target, int f_limit)
