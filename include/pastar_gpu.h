@@ -82,6 +82,9 @@ int pg_abi_version(void);
 /* Measurement helper: random 16-byte loads per second over a `bytes`-sized table (8 in flight per thread): the
  * measured hardware ceiling for the closed/open-table probe, reported by bench.py next to the kernel's rate. */
 int pg_bench_random_gather(int device, int64_t bytes, double *loads_per_sec);
+/* Measurement helper: DP-cell instruction groups (3 adds + one 3-input minimum, 8 independent chains per thread) per
+ * second on all SMs: the measured integer peak the pairwise-DP GCUPS are compared with. */
+int pg_bench_int_peak(int device, double *cells_per_sec);
 /* Run every later launch of this context on the caller's stream (cudaStream_t as void*; NULL = the legacy
  * default stream as everywhere in CUDA, (void*)-1 = back to the context's own non-blocking stream), e.g. torch's
  * current stream so that the caller's CUDA events bracket the work and NCCL collectives are ordered with it. */

@@ -87,6 +87,7 @@ def load_library():
         "pg_search_outbox": ([vp, i32, C.POINTER(vp), C.POINTER(i64)], i32),
         "pg_search_insert_dev": ([vp, vp, i64], i32),
         "pg_bench_random_gather": ([i32, i64, C.POINTER(C.c_double)], i32),
+        "pg_bench_int_peak": ([i32, C.POINTER(C.c_double)], i32),
         "pg_search_set_peers": ([vp, C.POINTER(vp), i32], i32),
         "pg_search_set_peer_counts": ([vp, C.POINTER(vp), i32, i32], i32),
         "pg_search_round_async": ([vp, C.c_int32], i32),
@@ -110,7 +111,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_bench_int_peak", "pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -187,6 +188,15 @@ def multi_search(gpus, table_capacity=0, batch_target=0, max_expansions=0, round
     if want_rows and res.finished:
         d["rows"] = [b.value.decode() for b in bufs]
     return d, [p.as_dict() for p in parts]
+
+
+def bench_int_peak(device=-1):
+    """DP-cell instruction groups (3 adds + min3) per second the integer pipes sustain: the pairwise DP's measured peak."""
+    out = C.c_double()
+    rc = load_library().pg_bench_int_peak(device, C.byref(out))
+    if rc:
+        raise PastarError(rc, "pg_bench_int_peak")
+    return out.value
 
 
 def host_weights(seqs):

@@ -80,6 +80,61 @@ extern "C" int pg_bench_random_gather(int device, int64_t bytes, double *loads_p
     return PG_OK;
 }
 
+// ---- measured integer peak for the pairwise DP's roofline: the DP cell is three adds and one three-input minimum
+// (IADD x3 + VIMNMX3); this kernel issues exactly that mix in 8 independent chains per thread, so it measures how
+// many DP-cell instruction groups per second the integer pipes sustain when nothing else limits them.
+namespace {
+__global__ void int_peak_kernel(int iters, int seed, int *out)
+{
+    int v[8], c = seed + (int)threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = seed * (k + 1) + (int)threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __vimin3_s32(v[k] + 30, v[(k + 1) & 7] + 29, v[(k + 3) & 7] + c); // one DP cell
+    }
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc ^= v[k];
+    if (acc == 0x7fffffff) out[0] = acc;
+}
+} // namespace
+
+extern "C" int pg_bench_int_peak(int device, double *cells_per_sec)
+{
+    if (!cells_per_sec) return PG_ERR_ARG;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PG_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return PG_ERR_CUDA;
+    int *out = nullptr;
+    if (cudaMalloc(&out, 64) != cudaSuccess) return PG_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int_peak_kernel<<<blocks, threads>>>(iters, 1, out);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0);
+        int_peak_kernel<<<blocks, threads>>>(iters, r + 2, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (err != cudaSuccess) return PG_ERR_CUDA;
+    *cells_per_sec = (double)blocks * threads * iters * 8 / (best * 1e-3);
+    return PG_OK;
+}
+
 extern "C" const char *pg_last_error(const pg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int pg_stage(pg_ctx *ctx, int which, size_t bytes, void **out)
