@@ -37,7 +37,7 @@ AA = "ACDEFGHIKLMNPQRSTVWY"
 METRIC, UNIT = "node_expansions_per_sec", "expansions/s"
 N_SEQ, LENGTH, SEED = 7, 500, 12345
 WORKLOAD = "synthetic N=7 x L=500 random protein (seed 12345), PAM250 costs, Altschul weights, budgeted A* search"
-CPU_STEP_POPS = 5000  # the reference arm's step: a bounded sample of the same search (100 steps = 0.5 M dequeues: 10-30 s of CPU work)
+CPU_STEP_POPS = 15000  # the reference arm's step: a bounded sample of the same search (100 steps = 1.5 M dequeues: ~15 s on the 16 host threads of the GPU box)
 
 
 def s7_seqs():
@@ -421,7 +421,7 @@ def run_ours(args, rank, world):
         # ---- CPU baseline beside it (bounded sample)
         try:
             threads = os.cpu_count() or 1
-            b = cpu_reference_run(threads, 100, 10)  # 0.5 M dequeues after 50 K warm-up: 10-30 s of CPU work
+            b = cpu_reference_run(threads, 100, 10)  # 1.5 M dequeues after 150 K warm-up: 10-30 s of CPU work
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # never lose the GPU numbers to a CPU-side hiccup
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
