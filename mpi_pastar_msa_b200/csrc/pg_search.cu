@@ -1984,7 +1984,14 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     uint64_t cap = cfg->table_capacity > 0 ? (uint64_t)cfg->table_capacity : 0;
     if (cap == 0) {
         cap = 1;
-        while (cap * 2 * (entry + 8) <= free_b / 2 && cap * 2 <= (1ull << 32)) cap *= 2; // about half of what is free
+        while (cap * 2 * (entry + 24) <= free_b / 2 && cap * 2 <= (1ull << 32)) cap *= 2; // table + open-list pool: about half of what is free
+        // ... but never more than twice the lattice itself: there are only prod(len + 1) coordinates (small inputs would
+        // otherwise spend their whole run time allocating and clearing tens of GB)
+        long double lattice = 1.0L;
+        for (int i = 0; i < ctx->n; i++) lattice *= (long double)(ctx->len[i] + 1);
+        uint64_t need = 1024;
+        while ((long double)need < 2.0L * lattice && need < cap) need *= 2;
+        cap = std::min(cap, need);
     } else {
         uint64_t c2 = 1024;
         while (c2 < cap) c2 *= 2;
