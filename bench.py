@@ -29,7 +29,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the image default prints the NCCL version)
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # default only: the driver may ask for INFO to check the ranks
 
 import numpy as np  # noqa: E402
 
@@ -140,6 +140,59 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# Known answers of the reference's own fixtures (reference arithmetic, optimal g*), used by the N > 1 parity gate.
+PARITY_INPUTS = {
+    "PF08184": (["QAVRYANGYTYDIETGQVSSPYTGRVYETKGKAPFYGFGFEHPYHYYPGYYHGYPHAFY",
+                 "QAVRYADGYTYDIETGQVSSPYTGRVYETKGKAPFYGFGFEHPYHYYPGYYHGYPHAFY",
+                 "QAVRYANGYTYDIETGQVSSPYTGRVYETKGKAPFYGFGFKYPYHYYPGYYHGYPHVFY"], 24450, 1 << 22, 64),
+    "kinase": ([
+        "NYIFGRTLGAGSFGVVRQARKLSTNEDVAIKILLKKALQGNNVQLQMLYEELSILQKLSHPNIVSFKDWFESKDKFYIVTQLATGGELFDRILSRGKFTEVDAVEIIVQILGAVEYMHSKNVVHRDLKPENVLYVDKSENSPLVIADFGIAKQLKGEEDLIYKAAGSLGYVAPEVLTQDGHGKPCDIWSIGVITYTLLCGYSPFIAESVEGFMEECTASRYPVTFHMPYWDNISIDVKRFILKALRLNPADRPTATELLDDPWITSK",
+        "DFEILKVIGRGAFSEVAVVKMKQTGQVYAMKIMNKWDMLKRGEVSCFREERDVLVNGDRRWITQLHFAFQDENYLYLVMEYYVGGDLLTLLSKFGERIPAEMARFYLAEIVMAIDSVHRLGYVHRDIKPDNILLDRCGHIRLADFGSCLKLRADGTVRSLVAVGTPDYLSPEILQAVGGGPGTGSYGPECDWWALGVFAYEMFYGQTPFYADSTAETYGKIVHYKEHLSLPLVDEGVPEEARDFIQRLLCPPETRLGRGGAGDFRTHPFFFGLDWD",
+        "TRKFKVELGRGESGTVYKGVLEDDRHVAVKKLENVRQGKEVFQAELSVIGRINHMNLVRIWGFCSEGSHRLLVSEYVENGSLANILFSEGGNILLDWEGRFNIALGVAKGLAYLHHECLEWVIHCDVKPENILLDQAFEPKITDFGLVKLLNRGGSTQNVSHVRGTLGYIAPEWVSSLPITAKVDVYSYGVVLLELLTGTRVSELVGGTDEVHSMLRKLVRMLSAKLEGEEQSWIDGYLDSKLNRPVNYVQARTLIKLAVSCL",
+        "QIRLTGRVGSGRFGNVSRGDYRGEAVAVKVFNALDEPAFHKETEIFETRMLRHPNVLRYIGSDRVDTGFVTELWLVTEYHPSGSLHDFLLENTVNIETYYNLMRSTASGLAFLHNQIGGSKESNKPAMAHRDIKSKNIMVKNDLTCAIGDLGLSLSKPEDAASDIIANENYKCGTVRYLAPEILNSTMQFTVFESYQCADVYSFSLVMWETLCRCEDGDVLPREAATVIPYIEWTDRDPQDAQMFDVVCTRRLRPTENPLWKDHPEMKHIMEI",
+        "HYKVGRRIGEGSFGVIFEGTNLLNNQQVAIKFEPRRSDAPQLRDEYRTYKLLAGCTGIPNVYYFGQEGLHNVLVIDLLGPSLEDLLDLCGRKFSVKTVAMAAKQMLARVQSIHEKSLVYRDIKPDNFLIGRPNSKNANMIYVVDFGMVKFYRDPVTKQHIPYREKKNLSGTARYMSINTHLGREQSRRDDLEALGHVFMYFLRGSLPWQGLKAATNKQKYERIGEKKQSTPLRELCAGFPEEFYKYMHYARNLAFDATPDYDYLQGLFSKVL"],
+        421546, 1 << 26, 16384),
+}
+
+
+def multi_gpu_parity(m, dist, world, rank, local):
+    """N > 1 parity on the real devices, before anything is timed: PF08184.fasta (BASELINE configs[2]) and kinase.fasta
+    solved to the optimality-preserving stop through PartitionedSearch.run() in all three exchange modes - NCCL
+    all-to-all of successor records (what replaces PAStarSender.cpp:62 / PAStarReceiver.cpp:55), P2P successor records,
+    P2P parent forwarding - each checked against the reference's optimal cost and by re-scoring the alignment."""
+    import torch
+    from mpi_pastar_msa_b200.dist import CudaEngine, CudaEngineP2P, PartitionedSearch
+    out, ok = {}, True
+    for name, (seqs, g_ref, cap, batch) in PARITY_INPUTS.items():
+        G = m.PastarGPU(seqs, device=local)
+        G.build_pair_tables()
+        G.configure_hash("FZORDER", 12)  # the reference's defaults (CoordHash.cpp:17-18)
+        per = {}
+        for mode in ("nccl_all_to_all", "p2p_records", "p2p_parent_forwarding"):
+            try:
+                if mode == "nccl_all_to_all":
+                    eng = CudaEngine(G, world, rank, cap, batch)
+                else:
+                    eng = CudaEngineP2P(G, world, rank, dist, cap, batch, forward=mode == "p2p_parent_forwarding")
+                drv = PartitionedSearch(eng, dist, seqs, lambda pos: int(G.owner(np.array(pos, dtype=np.uint16), world)[0]))
+                r = drv.run()
+                eng.end()
+                good = r["finished"] == 1 and r["g"] == g_ref and m.rescore_alignment(seqs, G.w_int, r["rows"]) == g_ref
+                per[mode] = {"ok": bool(good), "g": r["g"], "expansions": r["expansions"], "rounds": r["rounds"]}
+            except Exception as ex:  # a mode that cannot run is a failure, not a skip
+                per[mode] = {"ok": False, "error": repr(ex)}
+            t = torch.tensor([1 if per[mode]["ok"] else 0], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # every rank must agree
+            per[mode]["ok"] = bool(t.item())
+            ok = ok and per[mode]["ok"]
+        per["g_reference"] = g_ref
+        out[name] = per
+        G.close()
+    out["status"] = "ok" if ok else "FAILED"
+    out["n_gpus"] = world
+    return out
+
+
 def run_ours(args, rank, world):
     import torch
     import mpi_pastar_msa_b200 as m
@@ -151,6 +204,16 @@ def run_ours(args, rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    parity = None
+    if world > 1 and not args.skip_parity:
+        parity = multi_gpu_parity(m, dist, world, rank, local)
+        if parity["status"] != "ok":
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "n_gpus": world, "parity": parity, "error": "multi-GPU parity failed"}), flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            raise SystemExit(3)
 
     seqs = s7_seqs()
     batch, cap = args.batch, args.table_capacity
@@ -454,6 +517,8 @@ def run_ours(args, rank, world):
                        "rounds": r["rounds"], "wall_s": wall,
                        "includes": "per rank: host Altschul weights, context create, pairwise DP, P2P engine set-up, the partitioned search "
                                    "from the start node (PartitionedSearch.run), one status exchange every 8 rounds"}
+    if parity is not None:
+        line["parity"] = parity
     line["extra"] = extra
     if world == 1:
         G.close()
@@ -472,6 +537,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="open-list entries popped per round and GPU")
     ap.add_argument("--table-capacity", type=int, default=1 << 30)
+    ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the untimed PF08184 / kinase parity gate (profiling runs)")
     ap.add_argument("--hash-shift", type=int, default=17,
                     help="FZORDER owner-hash shift for N > 1 (the reference's -s, 0..21; its default 12 puts owner bits at bit 1 of two coordinates, 17 at bit 2 of three: fewer parents straddle partitions)")
     args = ap.parse_args()

@@ -190,6 +190,33 @@ def multi_search(gpus, table_capacity=0, batch_target=0, max_expansions=0, round
     return d, [p.as_dict() for p in parts]
 
 
+def rescore_alignment(seqs, w_int, rows, cost=None, gap_open=30, gap_ext=30, gap_gap=30):
+    """Host-side self check: the g of the path an alignment describes under the reference's cost model (Node.cpp:129-152,
+    240-243; weights (int)weightMatrix[x][y]).  A search result is valid iff its rows spell the sequences and re-score
+    to the reported optimum."""
+    cost = default_cost_table() if cost is None else np.asarray(cost).reshape(90, 90)
+    n, cols = len(seqs), len(rows[0])
+    if any(len(r) != cols for r in rows) or any(rows[i].replace("-", "") != seqs[i] for i in range(n)):
+        raise ValueError("alignment rows do not spell the input sequences")
+    prev, total = [1] * n, 0  # initial parenti: all ones (Sequences.cpp:75)
+    for c in range(cols):
+        mv = [0 if rows[i][c] == "-" else 1 for i in range(n)]
+        if not any(mv):
+            raise ValueError("empty alignment column")
+        for x in range(n - 1):
+            for y in range(x + 1, n):
+                if mv[x] and mv[y]:
+                    t = int(cost[ord(rows[x][c]), ord(rows[y][c])])
+                elif mv[x] or mv[y]:
+                    s = y if mv[x] else x          # the sequence that takes the gap
+                    t = gap_open if prev[s] else gap_ext
+                else:
+                    t = gap_gap
+                total += t * int(w_int[x][y])
+        prev = mv
+    return total
+
+
 def bench_int_peak(device=-1):
     """DP-cell instruction groups (3 adds + min3) per second the integer pipes sustain: the pairwise DP's measured peak."""
     out = C.c_double()

@@ -180,8 +180,6 @@ extern "C" int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens
         return PG_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
-    // the closed/open table is probed at random: fetch single 32 B sectors from HBM, not whole lines
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     ctx->n = n_seq;
     ctx->npairs = n_seq * (n_seq - 1) / 2;
     *out = ctx; // from here on errors leave a context whose message can be read; caller destroys it
@@ -228,6 +226,15 @@ extern "C" int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens
         pg_default_cost_table(hcost.data());
     bool nonneg = gap_open >= 0 && gap_ext >= 0;
     for (int32_t v : hcost) nonneg = nonneg && v >= 0;
+    ctx->cost_u8 = true;
+    for (int32_t v : hcost) ctx->cost_u8 = ctx->cost_u8 && v >= 0 && v <= 255;
+    {
+        bool seen[90] = {false};
+        for (const std::string &q : ctx->seqs)
+            for (unsigned char ch : q) seen[ch] = true;
+        ctx->n_alpha = 0;
+        for (bool b : seen) ctx->n_alpha += b ? 1 : 0;
+    }
     PG_CUDA(ctx, cudaMalloc(&ctx->d_cost, sizeof(int32_t) * 8100));
     PG_CUDA(ctx, cudaMemcpy(ctx->d_cost, hcost.data(), sizeof(int32_t) * 8100, cudaMemcpyHostToDevice));
     dp.cost = ctx->d_cost;

@@ -212,14 +212,14 @@ int launch_expand_n(pg_ctx *ctx, const void *d_parents, int64_t k, int vec_size,
     using C = ExpCfg<N>;
     constexpr int GROUPS = 256 / C::LP;
     const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the dynamic shared memory opt-in is per DEVICE state: cached in the context (one context per device), never in a
+    // process-wide static (pg_multi_search drives several devices from one process)
+    int &occ = ctx->occ_expand_batch;
+    if (!occ) {
         PG_CUDA(ctx, cudaFuncSetAttribute(expand_batch_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_batch_kernel<N>, 256, smem));
+        if (occ < 1) occ = 1;
     }
-    int occ = 1;
-    PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_batch_kernel<N>, 256, smem));
-    if (occ < 1) occ = 1;
     long long want = (k + GROUPS - 1) / GROUPS;
     long long grid = std::min<long long>(want, (long long)ctx->sm_count * occ); // persistent: a multiple of the SM count
     if (grid < 1) grid = 1;

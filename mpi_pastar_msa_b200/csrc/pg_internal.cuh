@@ -43,7 +43,7 @@ struct SearchCtrl {          // lives in device memory; mirrored to pinned host 
     int32_t best_goal;       // INT32_MAX until the goal has been generated
     int32_t prune_limit;     // successors with f >= this are dropped (upper bound + 1)
     int32_t done;            // 1 optimal, 2 open list exhausted
-    int32_t error;           // 1 table full, 2 pool exhausted, 3 f range exceeded
+    int32_t error;           // 1 table full, 2 pool exhausted, 3 f beyond the bucket range, 4 outbox / survivor list overflow, 5 f below h(start)
     int32_t batch_n;         // parents selected for the current round
     int32_t plan_n;          // plan entries of the current round
     int32_t min_open_f;      // f of the first non-empty bucket after the last select (INT32_MAX if none)
@@ -68,6 +68,8 @@ struct pg_ctx {
     void *d_tables = nullptr;
     size_t table_cells = 0;
     bool tables_built = false;
+    bool cost_u8 = false;      // every entry of the cost table is in 0..255 (the linear-gap DP kernel packs them in bytes)
+    int n_alpha = 0;           // distinct residues over all sequences
     int sm_count = PG_SM_COUNT_B200;
     cudaStream_t stream = nullptr;       // stream all launches go to (own_stream unless pg_ctx_set_stream)
     cudaStream_t own_stream = nullptr;
@@ -76,6 +78,10 @@ struct pg_ctx {
     void *d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes[2] = {0, 0};
     SearchState *search = nullptr;
+    // resident CTAs per SM of the kernels that opt in to > 48 KB of dynamic shared memory; 0 = attribute not set yet on
+    // this context's device (N and the key width are fixed per context, so one slot per kernel / mode is enough)
+    int occ_expand_batch = 0;
+    int occ_expand_probe[3] = {0, 0, 0};
     std::string err;
 };
 

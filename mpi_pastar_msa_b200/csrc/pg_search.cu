@@ -361,8 +361,12 @@ __device__ __noinline__ void bucket_place_slow(const DevSearch &d, int b, uint32
 // bucket index of f, or -1 (error raised) when f is beyond the bucket range
 __device__ __forceinline__ int bucket_of(const DevSearch &d, int f)
 {
-    int b = f - d.f0; // f0 / f_range are constants of the search: read from the kernel parameters, not from the control
-    if (b < 0) b = 0; // block whose line is busy with counter atomics; b < 0 cannot happen with a consistent heuristic
+    const int b = f - d.f0; // f0 / f_range are constants of the search: read from the kernel parameters, not from the control
+                            // block whose line is busy with counter atomics
+    if (b < 0) { // f below h(start): the heuristic is not consistent for this cost model; reported, never clamped
+        d.ctrl->error = 5;
+        return -1;
+    }
     if (b >= d.f_range) {
         d.ctrl->error = 3;
         return -1;
@@ -739,7 +743,10 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
     __shared__ int s_wtot[8];
     __shared__ unsigned long long s_base;
     SearchCtrl *c = d.ctrl;
-    const int batch_n = (c->done || c->error) ? 0 : c->batch_n;
+    __shared__ int s_batch_n;
+    if (threadIdx.x == 0) s_batch_n = (c->done || c->error) ? 0 : c->batch_n; // read once per CTA: barriers follow
+    __syncthreads();
+    const int batch_n = s_batch_n;
     if (batch_n == 0) return;
     const int plan_n = c->plan_n;
     const bool plan_sm = plan_n <= PLAN_SM;
@@ -833,9 +840,12 @@ __global__ void __launch_bounds__(256) forward_kernel(const __grid_constant__ De
                                                       const __grid_constant__ OwnerArgs oa)
 {
     SearchCtrl *c = d.ctrl;
-    if (c->done || c->error) return;
-    const long long live_n = (long long)c->live_n;
     const int lane = threadIdx.x & 31;
+    {   // warp-uniform early exit (c->error may be raised by another CTA of this launch; ballots follow)
+        int skip = lane == 0 ? (c->done || c->error) : 0;
+        if (__shfl_sync(0xffffffffu, skip, 0)) return;
+    }
+    const long long live_n = (long long)c->live_n;
     const unsigned lt = (1u << lane) - 1u;
     for (long long base = (long long)blockIdx.x * 256; base < live_n; base += (long long)gridDim.x * 256) {
         const long long i0 = base + threadIdx.x;
@@ -959,13 +969,19 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     __shared__ unsigned char s_mod[MULTI ? 256 : 1]; // owner word -> partition
 
     SearchCtrl *c = d.ctrl;
-    if (c->done || c->error) return;
-    {
+    // the flags are read ONCE per CTA (other CTAs of this launch may raise c->error while this one starts; the warps of a
+    // CTA must agree on the early return because barriers follow)
+    __shared__ int s_skip;
+    if (threadIdx.x == 0) {
         unsigned long long any = 0;
         for (int rg = 0; rg < ps.n; rg++) any |= *ps.count[rg];
-        if (any == 0) return;
+        s_skip = (c->done || c->error || any == 0) ? 1 : 0;
     }
-    const int limit = min(c->prune_limit, c->best_goal);
+    __syncthreads();
+    if (s_skip) return;
+    const int prune = c->prune_limit;
+    const int best0 = c->best_goal;
+    const int limit = min(prune, best0);
 
     pg_load_pair_meta(p, meta);
     for (int hi = threadIdx.x; hi < C::H; hi += blockDim.x) {
@@ -1120,8 +1136,15 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                         const int f = gn + vh[i] + s_hhh[high];
                         n_gen++;
                         const bool is_goal = mask == goal_mask;
-                        if (is_goal) atomicMin(&c->best_goal, gn);
-                        if (f >= limit && !is_goal) {
+                        // a goal (f == g) beyond the upper bound can never be optimal - UB is the cost of a valid
+                        // alignment - and one worse than the best goal known is useless: both are dropped like any
+                        // other successor, so nothing past the bucket range is ever pushed
+                        bool drop = f >= limit;
+                        if (is_goal) {
+                            drop = gn >= prune || gn > best0;
+                            if (!drop) atomicMin(&c->best_goal, gn);
+                        }
+                        if (drop) {
                             n_pruned++;
                             v = false;
                         }
@@ -1271,12 +1294,16 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
     constexpr int PF = 4;
     enum { DONE = 0, KEY = 1, VAL = 2, PUSH = 3, WALK = 4 };
     SearchCtrl *c = d.ctrl;
-    if (c->error) return;
+    {   // warp-uniform early exit: other CTAs of this launch may raise c->error, and warp-level ballots follow
+        int skip = (threadIdx.x & 31) == 0 ? c->error : 0;
+        if (__shfl_sync(0xffffffffu, skip, 0)) return;
+    }
     const long long n = (long long)min(*n_ptr, n_max);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->table_used, (unsigned long long)n); // records seen by insert kernels
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     int min_b = INT_MAX;
-    const int limit = min(c->prune_limit, c->best_goal);
+    const int prune = c->prune_limit;
+    const int limit = min(prune, c->best_goal);
     __shared__ unsigned long long s_walk[8 * RING_CAP * XW];
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -1328,8 +1355,12 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
             if (state[j] == DONE) continue;
             bool is_goal = key[j].lo == d.goal_lo;
             if constexpr (KEYW == 2) is_goal = is_goal && key[j].hi == d.goal_hi;
-            if (is_goal) atomicMin(&c->best_goal, (int)(unsigned)(gf[j] >> 32));
-            if ((int)(unsigned)gf[j] >= limit && !is_goal) {
+            bool drop = (int)(unsigned)gf[j] >= limit;
+            if (is_goal) { // kept iff within the upper bound and at least as good as every goal seen so far (f == g)
+                const int gg = (int)(unsigned)(gf[j] >> 32);
+                drop = gg >= prune || gg > atomicMin(&c->best_goal, gg);
+            }
+            if (drop) {
                 state[j] = DONE;
                 continue;
             }
@@ -1714,7 +1745,8 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
     constexpr int XW = KEYW == 1 ? 3 : 4;
     const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + 8 * 8 * RING_CAP * XW +
                         sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
-    static int occ = 0;
+    // per-device state (cudaFuncSetAttribute applies to the current device only): cached per context and kernel mode
+    int &occ = ctx->occ_expand_probe[MODE];
     if (!occ) {
         PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, MODE>, 256, smem));
@@ -1900,6 +1932,8 @@ int sync_ctrl(pg_ctx *ctx)
         return pg_fail(ctx, PG_ERR_CAPACITY, "open-list chunk pool exhausted: raise pg_search_config.table_capacity");
     case 3:
         return pg_fail(ctx, PG_ERR_CAPACITY, "f exceeded the bucket range");
+    case 5:
+        return pg_fail(ctx, PG_ERR_UNSUPPORTED, "a successor's f fell below h(start): the heuristic is not consistent for this cost model");
     default:
         return pg_fail(ctx, PG_ERR_CAPACITY, "outbox overflow: lower batch_target");
     }
@@ -2022,7 +2056,8 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     s->ub = h2[1];
     long long range = (long long)s->ub - s->f0 + 2;
     if (range < 2) range = 2;
-    if (range > (1ll << 27)) range = 1ll << 27; // 1 GiB of bucket heads at most; deeper f is pruned
+    if (range > (1ll << 27)) // 1 GiB of bucket heads at most: a wider f range is refused, never clamped
+        return pg_fail(ctx, PG_ERR_UNSUPPORTED, "f range (upper bound - h(start)) exceeds 2^27 open-list buckets");
     s->f_range = (int)range;
 
     // ---- allocations

@@ -211,6 +211,8 @@ class PartitionedSearch:
             if int(v[0]) != 1:
                 raise RuntimeError("backtrace lost the parent chain at %s" % (pos,))
             mask = int(v[2])
+            if mask <= 0:  # a zero move mask would never reach the origin
+                raise RuntimeError("backtrace found an entry without a parent move at %s" % (pos,))
             cols.append(mask)
             pos = [p - ((mask >> i) & 1) for i, p in enumerate(pos)]
         rows = [[] for _ in range(n)]

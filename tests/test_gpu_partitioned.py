@@ -188,3 +188,57 @@ def test_p2p_modes_wide_key(gpu_lib, mode):
     from conftest import WIDE_CASES
     r = p2p_search(gpu_lib, WIDE_CASES["fam10x100"], 4, 4096, "FZORDER", 6, mode, cap=1 << 24)
     assert r["g"] == KNOWN_OPT["fam10x100"], r
+
+
+def _n_devices():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("name,parts,batch,ht,sh", [
+    ("PF08184", 2, 64, "FZORDER", 12), ("kinase", 2, 16384, "FZORDER", 12), ("fam5x60", 2, 256, "FZORDER", 0),
+    ("fam14x6", 2, 256, "FZORDER", 1), ("fam16x5", 2, 128, "FZORDER", 0), ("fam8x20", 4, 4096, "PZORDER", 1),
+    ("fam4x150", 8, 4096, "FZORDER", 12)])
+def test_multi_search_distinct_devices(gpu_lib, name, parts, batch, ht, sh):
+    """pg_multi_search with one context per REAL device (needs >= parts GPUs: `gpurun --gpus N`): peer-mapped inboxes over
+    NVLink, cross-device visibility of forward_kernel's stores, the stream-wait barrier.  N = 14 / 16 need more than
+    48 KB of dynamic shared memory in the expand kernel: the opt-in is per device and must be made on every device."""
+    if _n_devices() < parts:
+        pytest.skip("needs %d GPUs" % parts)
+    seqs = CASES[name]
+    ref = KNOWN_OPT.get(name) or O.Problem(seqs).astar(want_rows=False)["g"]
+    Gs = []
+    for dev in range(parts):
+        G = gpu_lib.PastarGPU(seqs, device=dev)
+        G.build_pair_tables()
+        G.configure_hash(ht, sh)
+        Gs.append(G)
+    tot, per = gpu_lib.multi_search(Gs, table_capacity=1 << 24, batch_target=batch)
+    assert tot["finished"] == 1 and tot["g"] == ref, tot
+    w = gpu_lib.host_weights(seqs).astype(np.int32)
+    assert weighted_sp_score(seqs, w, tot["rows"]) == ref
+    assert gpu_lib.rescore_alignment(seqs, w, tot["rows"]) == ref
+    assert sum(p["expansions"] for p in per) == tot["expansions"]
+    for G in Gs:
+        G.close()
+
+
+@pytest.mark.parametrize("name", ["fam14x6", "fam16x5"])
+def test_multi_search_wide_n_one_device(gpu_lib, name):
+    """N = 14 / 16 through pg_multi_search on one device (two contexts): each context opts its kernels in to > 48 KB of
+    dynamic shared memory itself (the cache is per context, not per process)."""
+    seqs = CASES[name]
+    ref = KNOWN_OPT.get(name) or O.Problem(seqs).astar(want_rows=False)["g"]
+    Gs = []
+    for _ in range(2):
+        G = gpu_lib.PastarGPU(seqs)
+        G.build_pair_tables()
+        G.configure_hash("FZORDER", 1)
+        Gs.append(G)
+    tot, _ = gpu_lib.multi_search(Gs, table_capacity=1 << 22, batch_target=256)
+    assert tot["finished"] == 1 and tot["g"] == ref, tot
+    for G in Gs:
+        G.close()
