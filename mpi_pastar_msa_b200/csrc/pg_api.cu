@@ -256,12 +256,13 @@ extern "C" int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens
             g.b = j;
             g.rows = lens[i] + 1;
             g.cols = lens[j] + 1;
+            g.pitch = (g.cols + 7) & ~7;
             g.offset = cells;
-            cells += ((size_t)g.rows * g.cols + 127) & ~size_t(127);
+            cells += ((size_t)g.rows * g.pitch + 127) & ~size_t(127);
             ctx->pairs.push_back(g);
             dp.pa[k] = (uint8_t)i;
             dp.pb[k] = (uint8_t)j;
-            dp.cols[k] = g.cols;
+            dp.cols[k] = g.pitch;
             dp.w[k] = w_int ? w_int[i * n_seq + j] : 1;
             bound = std::max(bound, (long long)std::max(gap_open, gap_ext) * (lens[i] + lens[j]));
         }
@@ -321,12 +322,12 @@ extern "C" int pg_copy_pair_table(pg_ctx *ctx, int pair, int32_t *out)
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     const PairGeom &g = ctx->pairs[pair];
     const size_t n = (size_t)g.rows * g.cols;
-    if (ctx->dp.cell16) {
+    if (ctx->dp.cell16) { // stored rows are pitched: gather the logical rows x cols
         std::vector<uint16_t> tmp(n);
-        PG_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->dp.table[pair], n * 2, cudaMemcpyDeviceToHost));
+        PG_CUDA(ctx, cudaMemcpy2D(tmp.data(), (size_t)g.cols * 2, ctx->dp.table[pair], (size_t)g.pitch * 2, (size_t)g.cols * 2, g.rows, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; i++) out[i] = tmp[i];
     } else {
-        PG_CUDA(ctx, cudaMemcpy(out, ctx->dp.table[pair], n * 4, cudaMemcpyDeviceToHost));
+        PG_CUDA(ctx, cudaMemcpy2D(out, (size_t)g.cols * 4, ctx->dp.table[pair], (size_t)g.pitch * 4, (size_t)g.cols * 4, g.rows, cudaMemcpyDeviceToHost));
     }
     return PG_OK;
 }

@@ -22,7 +22,7 @@ struct DevProblem {
     int hash_type, hash_shift;
     int len[PG_MAX_SEQ];
     int w[PG_MAX_PAIRS];               // (int)weightMatrix[x][y] per pair, (i<j) order
-    int cols[PG_MAX_PAIRS];            // len[y] + 1
+    int cols[PG_MAX_PAIRS];            // row pitch of the pair's table in cells: len[y] + 1 rounded up to a multiple of 8
     uint8_t pa[PG_MAX_PAIRS], pb[PG_MAX_PAIRS]; // pair -> (x, y), x < y
     const uint8_t *seq[PG_MAX_SEQ];    // residues, len+1 bytes, trailing 0 (Node.cpp:225 reads seq[len])
     const void *table[PG_MAX_PAIRS];   // reverse DP tables, row-major (len[x]+1) x (len[y]+1)
@@ -32,6 +32,7 @@ struct DevProblem {
 struct PairGeom {
     int a, b;       // sequence indices, a < b
     int rows, cols; // len+1
+    int pitch;      // cells per stored row (cols rounded up to a multiple of 8: rows start 16-byte aligned)
     size_t offset;  // cell offset into the table arena
 };
 

@@ -25,7 +25,9 @@
 // Bound: integer ALU / dependency latency (min-plus; no tensor-core shape).
 // Bytes: one cell written once (4 B, or 2 B when 30*(L1+L2) < 65536).
 #include <algorithm>
+#include <cstddef>
 #include <cstdlib>
+#include <type_traits>
 
 #include "pg_internal.cuh"
 
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(32 * DP_MAXW, 1) pair_dp_kernel(const __grid_c
     const int pair = blockIdx.x;
     const int sa = p.pa[pair], sb = p.pb[pair];
     const int L1 = p.len[sa], L2 = p.len[sb];
-    const int cols = L2 + 1;
+    const int cols = p.cols[pair]; // row pitch (>= L2 + 1)
     TC *M = const_cast<TC *>(reinterpret_cast<const TC *>(p.table[pair]));
     const uint8_t *s1 = p.seq[sa];
     const uint8_t *s2 = p.seq[sb];
@@ -211,89 +213,172 @@ __global__ void __launch_bounds__(32 * DP_MAXW, 1) pair_dp_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------------------------------
 // Linear-gap fast path (GapOpen == GapExtension, the reference's constants, Cost.h:13; all costs in 0..255).
 //
-// Same mapping as above (one CTA per pair, a warp per band of 32*R rows, lane = R rows, anti-diagonal wavefront, bands
-// chained through shared-memory rings), but the step is cut to what the recurrence needs; the old kernel issued ~200
-// warp instructions per step and was bound by instruction issue, not by the min-plus chain:
-//   * the column residue travels WITH the wavefront: lane l-1 hands lane l one word {top value, residue code} by a
-//     single __shfl_up; lane 0's inputs {cell of the row below the band, residue code} are fetched 16 steps at a time
-//     (one lane each) and broadcast by __shfl;
+// Same mapping as the general kernel (one CTA per pair, a warp per band of 32*R rows, anti-diagonal wavefront over the
+// lanes, bands chained through shared-memory rings), rebuilt around what one warp can issue: the general kernel spends
+// ~200 dependent warp instructions per single-column step.  Here
+//   * a lane computes a register block of R x C = 4 x 4 cells per super-step (C columns of its R rows): 16 cells whose
+//     dependency DAG is only R + C - 1 = 7 cells deep, so one lane-to-lane hand-over (C __shfl_up of the block's top
+//     row, 24 cycles each, pipelined) is paid per FOUR columns and the cells in between overlap;
+//   * a cell is min(min(below, right) + gap, diag + cost): PRMT (cost byte) + IADD + VIMNMX + VIADDMNMX;
 //   * substitution costs come from a per-warp table T[code][lane] = the costs of the lane's R row residues against
-//     residue `code`, packed one byte each: one conflict-free shared load per step for all R cells;
-//   * a cell is min(min(below, right) + gap, diag + cost): VIMNMX + VIADDMNMX on the dependent chain;
-//   * results go to a per-warp tile indexed by step (no per-lane address arithmetic) and leave as coalesced row
-//     segments every 32 steps; 16-step blocks are fully unrolled, blocks in which every lane is inside the table run
-//     without bounds checks.
+//     column residue `code`, one byte each; the column codes sit in shared memory in sweep order (one aligned 32-bit
+//     load gives a super-step's four codes); none of this is on the dependent chain;
+//   * the table is swept on a 4-column grid aligned to memory: columns j > L2 are virtual +INF, the border column
+//     j = L2 falls out of the recurrence itself, rows are pitched to a multiple of 8 cells, so every block leaves as
+//     aligned 8 / 16-byte vectors: registers -> shared tile (STS.128) -> global (one vector per lane, 4 rows x 32
+//     columns per warp instruction) every 8 super-steps;
+//   * 4 super-steps are fully unrolled; chunks in which every lane is inside the table run without bounds checks.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int FD_RING = 256; // ring entries per warp (power of two)
-constexpr int FD_CHUNK = 16; // steps per unrolled block = ring fetch / publish granularity
-constexpr int FD_TW = 32;    // tile width in steps = flush period
-constexpr int FD_RS = FD_TW + 1;
+constexpr int FD_R = 4;       // rows per lane
+constexpr int FD_C = 4;       // columns per super-step
+constexpr int FD_SS = 4;      // super-steps per unrolled chunk (ring fetch / publish granularity: 16 columns)
+constexpr int FD_WIN = 8;     // super-steps per flush window (32 columns)
+constexpr int FD_RING = 256;  // ring entries (columns) per warp, power of two
+constexpr int FD_CCPAD = 160; // padding of the column-code array on both sides (lanes ahead of / behind the table)
+constexpr int FD_INF = 1 << 28;
+// Ordering between a warp's ring accesses and its progress counters.  Both live in shared memory, and one warp's
+// shared-memory accesses are performed in program order by the SM, so only the COMPILER must be kept from moving them:
+// a MEMBAR.SC.CTA here (what __threadfence_block() emits) also waits for the flush's global stores - measured at about
+// 1000 cycles, twice per 16 columns, 80 % of the first version's run time.
+#define FD_ORDER() asm volatile("" ::: "memory")
 
-template <typename TC, int R, bool CHECK>
-__device__ __forceinline__ void fd_steps(int s0, int lane, int L2, int gap, const uint32_t *Tw, TC *tcol, int (&right)[R], int &diag0,
-                                         int &out_pk, int in_pk, bool wr_ring, volatile int32_t *ring_out, unsigned out_base)
+template <typename TC>
+struct FdGeom {
+    static constexpr int UNIT = FD_R * FD_C * (int)sizeof(TC); // bytes one lane stages per super-step
+    static constexpr int SG = 32 * UNIT + 16;                  // bytes per super-step slot of the tile (padded: bank spread)
+    static constexpr int TILE = FD_WIN * SG;                   // bytes per warp
+};
+
+// predicated vector stores: a branch per store costs more than the store
+__device__ __forceinline__ void fd_store_if(bool ok, void *ptr, const uint2 &v)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.global.v2.u32 [%1], {%2, %3};\n\t}" ::"r"((int)ok), "l"(ptr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void fd_store_if(bool ok, void *ptr, const int4 &v)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.global.v4.u32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"((int)ok), "l"(ptr), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// One chunk = FD_SS super-steps.  Every lane computes in every super-step: lanes ahead of the table (column group g < 0)
+// or past it (g >= G) work on garbage that nothing valid ever reads - the wavefront hands a lane only blocks of the
+// group it is about to compute - so the chunk has no bounds checks and no divergence.  RAMP (the first 32 super-steps of
+// a band): a lane's running state is reset when it enters the table (g == 0).
+template <typename TC, bool RAMP>
+__device__ __forceinline__ void fd_chunk(int u0, int lane, int G, int gap, const uint32_t *Tw, const uint8_t *cc_lane, unsigned char *tunit,
+                                         const int *inp, int (&right)[FD_R], int &diag0, int (&top)[FD_C], uint32_t (&cwn)[FD_C], bool wr_ring,
+                                         int *ring_out, unsigned out_pos)
 {
 #pragma unroll
-    for (int t = 0; t < FD_CHUNK; t++) {
-        const int s = s0 + t;
-        const int up = __shfl_up_sync(0xffffffffu, out_pk, 1);
-        const int in0 = __shfl_sync(0xffffffffu, in_pk, t);
-        const int cur = lane == 0 ? in0 : up;
-        const int kc = s - lane; // my column counter: column L2-1-kc
-        if (!CHECK || (unsigned)kc < (unsigned)L2) {
-            const int code = cur & 127;
-            int below = cur >> 7;
-            const uint32_t cw = Tw[code * 32];
-            int dg = diag0;
-            diag0 = below;
+    for (int t = 0; t < FD_SS; t++) {
+        int up[FD_C];
 #pragma unroll
-            for (int k = 0; k < R; k++) {
-                const int c = (int)((cw >> (8 * k)) & 0xffu);
-                const int m = __viaddmin_s32(min(below, right[k]), gap, dg + c);
-                dg = right[k];
-                right[k] = m;
-                below = m;
-                tcol[k * FD_RS + t] = (TC)m;
-            }
-            out_pk = (below << 7) | code;
-            if (wr_ring) ring_out[(out_base + (unsigned)kc) & (FD_RING - 1)] = below;
+        for (int i = 0; i < FD_C; i++) up[i] = __shfl_up_sync(0xffffffffu, top[i], 1);
+        const int4 in4 = *reinterpret_cast<const int4 *>(inp + FD_C * t); // lane 0's row below (uniform address: broadcast)
+        const int g = u0 + t - lane;                                      // my column group: columns Lp-1-4g-i, i = 0..3
+        uint32_t cw[FD_C];
+#pragma unroll
+        for (int i = 0; i < FD_C; i++) cw[i] = cwn[i];
+        {   // the next super-step's cost words travel while this block is computed
+            const uint32_t codes = *reinterpret_cast<const uint32_t *>(cc_lane + FD_C * (t + 1));
+#pragma unroll
+            for (int i = 0; i < FD_C; i++) cwn[i] = Tw[((codes >> (8 * i)) & 0xffu) * 32];
         }
+        if (RAMP && g == 0) {
+#pragma unroll
+            for (int k = 0; k < FD_R; k++) right[k] = FD_INF; // virtual column Lp
+            diag0 = FD_INF;
+        }
+        int prev[FD_C];
+        prev[0] = lane == 0 ? in4.x : up[0];
+        prev[1] = lane == 0 ? in4.y : up[1];
+        prev[2] = lane == 0 ? in4.z : up[2];
+        prev[3] = lane == 0 ? in4.w : up[3];
+        int prevR = diag0; // cell diagonally below-right of (row 0, column 0)
+        diag0 = prev[FD_C - 1];
+        int m[FD_R][FD_C];
+#pragma unroll
+        for (int k = 0; k < FD_R; k++) {
+            int d = prevR, r = right[k];
+            prevR = r;
+#pragma unroll
+            for (int i = 0; i < FD_C; i++) {
+                const int c = (int)__byte_perm(cw[i], 0u, 0x4440u | (unsigned)k);
+                const int v = __viaddmin_s32(min(prev[i], r), gap, d + c);
+                d = prev[i];
+                prev[i] = v;
+                r = v;
+                m[k][i] = v;
+            }
+            right[k] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < FD_C; i++) top[i] = prev[i];
+        // ---- stage the block: memory order is ascending column, i.e. i = 3, 2, 1, 0
+        unsigned char *tu = tunit + t * FdGeom<TC>::SG;
+        if constexpr (sizeof(TC) == 2) {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < FD_R; k++) {
+                w[2 * k] = __byte_perm((unsigned)m[k][3], (unsigned)m[k][2], 0x5410u);
+                w[2 * k + 1] = __byte_perm((unsigned)m[k][1], (unsigned)m[k][0], 0x5410u);
+            }
+            reinterpret_cast<uint4 *>(tu)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4 *>(tu)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < FD_R; k++) reinterpret_cast<int4 *>(tu)[k] = make_int4(m[k][3], m[k][2], m[k][1], m[k][0]);
+        }
+        if (wr_ring && (unsigned)g < (unsigned)G)
+            *reinterpret_cast<int4 *>(ring_out + ((out_pos + (unsigned)(FD_C * g)) & (FD_RING - 1))) = make_int4(top[0], top[1], top[2], top[3]);
     }
 }
 
 template <typename TC, int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __grid_constant__ DevProblem p, int warps, int nalpha)
+__global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __grid_constant__ DevProblem p, int warps, int nalpha, int cc_bytes)
 {
-    constexpr int R = 4, BAND = 32 * R;
+    constexpr int R = FD_R, C = FD_C, BAND = 32 * R;
+    using GEO = FdGeom<TC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint8_t *s_cost8 = smem_raw;                                                  // 90 x 90 costs, one byte each
-    uint8_t *s_code = s_cost8 + 8112;                                             // residue -> dense code (96)
-    uint8_t *s_alpha = s_code + 96;                                               // dense code -> residue (96)
-    volatile int32_t *s_ring = reinterpret_cast<volatile int32_t *>(s_alpha + 96); // [warps][FD_RING]
-    volatile unsigned *s_prod = reinterpret_cast<volatile unsigned *>(s_ring + warps * FD_RING);
+    uint8_t *s_cost8 = smem_raw;                                   // 90 x 90 costs, one byte each (8112 reserved)
+    uint8_t *s_code = s_cost8 + 8112;                              // residue -> dense code (96)
+    uint8_t *s_alpha = s_code + 96;                                // dense code -> residue (96)
+    int *s_ring = reinterpret_cast<int *>(s_alpha + 96);           // [warps][FD_RING]
+    int *s_bord = s_ring + warps * FD_RING;                        // [warps][16]: band 0's row below (the border row)
+    volatile unsigned *s_prod = reinterpret_cast<volatile unsigned *>(s_bord + warps * 16);
     volatile unsigned *s_cons = s_prod + warps;
-    uint32_t *s_T = const_cast<uint32_t *>(reinterpret_cast<volatile uint32_t *>(s_cons + warps)); // [warps][nalpha][32]
-    TC *s_tile = reinterpret_cast<TC *>(s_T + (size_t)warps * nalpha * 32);                        // [warps][BAND][FD_RS]
+    uint32_t *s_T = const_cast<uint32_t *>(reinterpret_cast<volatile uint32_t *>(s_cons + warps)) + ((warps & 1) ? 2 : 0); // keep 16-byte alignment
+    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_T + (size_t)warps * nalpha * 32);                                          // column codes, sweep order
+    unsigned char *s_tile = s_cc + cc_bytes;                                                                                  // [warps][GEO::TILE]
     __shared__ int s_na;
 
     const int pair = blockIdx.x;
     const int sa = p.pa[pair], sb = p.pb[pair];
     const int L1 = p.len[sa], L2 = p.len[sb];
-    const int cols = L2 + 1;
+    const int pitch = p.cols[pair];
     TC *M = const_cast<TC *>(reinterpret_cast<const TC *>(p.table[pair]));
     const uint8_t *s1 = p.seq[sa];
     const uint8_t *s2 = p.seq[sb];
-    const int gap = p.gap_open; // == p.gap_ext on this path
+    const int gap = p.gap_open;                 // == p.gap_ext on this path
+    const int Lp = (L2 + 1 + C - 1) & ~(C - 1); // swept columns: 0 .. L2 (border column included), padded to the 4-column grid
+    const int G = Lp / C;                       // column groups
 
-    for (int i = threadIdx.x; i < 90 * 90; i += blockDim.x) s_cost8[i] = (uint8_t)__ldg(p.cost + i);
-    if (threadIdx.x < 96) s_code[threadIdx.x] = 0;
+    {   // cost table -> bytes (8100 = 2025 x 4 entries)
+        const int4 *src = reinterpret_cast<const int4 *>(p.cost);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_cost8);
+        for (int i = threadIdx.x; i < 2025; i += blockDim.x) {
+            const int4 v = __ldg(src + i);
+            dst[i] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) | ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+        }
+    }
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) s_code[i] = 0;
     if (threadIdx.x < warps) {
         s_prod[threadIdx.x] = 0;
         s_cons[threadIdx.x] = 0;
     }
-    // borders, PairAlign.cpp:142-160
-    for (int j = threadIdx.x; j <= L2; j += blockDim.x) M[(size_t)L1 * cols + j] = (TC)(j == L2 ? 0 : gap + (L2 - 1 - j) * gap);
-    for (int i = threadIdx.x; i < L1; i += blockDim.x) M[(size_t)i * cols + L2] = (TC)(gap + (L1 - 1 - i) * gap);
+    // bottom border row M[L1][j] = gap * (L2 - j), PairAlign.cpp:142-160 (the border column comes out of the sweep)
+    for (int j = threadIdx.x; j <= L2; j += blockDim.x) M[(size_t)L1 * pitch + j] = (TC)(gap * (L2 - j));
     __syncthreads();
     for (int j = threadIdx.x; j < L2; j += blockDim.x) s_code[s2[j]] = 1; // residues that occur in the column sequence
     __syncthreads();
@@ -308,30 +393,37 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
         s_na = na;
     }
     __syncthreads();
-    if (L2 == 0) return;
+    // column codes in sweep order: entry FD_CCPAD + kc is column Lp-1-kc (0 for the border / virtual columns and the padding)
+    for (int i = threadIdx.x; i < cc_bytes; i += blockDim.x) {
+        const int j = Lp - 1 - (i - FD_CCPAD);
+        s_cc[i] = (j >= 0 && j < L2) ? s_code[s2[j]] : (uint8_t)0;
+    }
+    __syncthreads();
     const int na = s_na;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nbands = (L1 + BAND - 1) / BAND;
     uint32_t *Tw = s_T + (size_t)warp * nalpha * 32 + lane;
-    TC *tile = s_tile + (size_t)warp * BAND * FD_RS;
-    volatile int32_t *ring_out = s_ring + warp * FD_RING;
+    unsigned char *tile = s_tile + (size_t)warp * GEO::TILE;
+    int *ring_out = s_ring + warp * FD_RING;
     const int pwarp = (warp + warps - 1) % warps;
-    volatile int32_t *ring_in = s_ring + pwarp * FD_RING;
-    const int nsteps = L2 + 31;
-    const int nchunks = (nsteps + FD_CHUNK - 1) / FD_CHUNK;
+    const int *ring_in = s_ring + pwarp * FD_RING;
+    int *bord = s_bord + warp * 16;
+    const int nss = G + 31;                              // super-steps per band
+    const int nchunks = (nss + FD_SS - 1) / FD_SS;
+    const unsigned span = (unsigned)((Lp + 15) & ~15);   // ring positions per band (a chunk's 16 never wrap)
 
     for (int band = warp; band < nbands; band += warps) {
         // lane l owns rows r0, r0-1, ..., r0-(R-1); k = 0 is the lowest of them, lane 0 / k 0 the bottom row of the band
         const int r0 = L1 - 1 - (band * BAND + lane * R);
-        int right[R];
+        int right[R], top[C];
         {
             int a[R];
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 const int r = r0 - k;
                 a[k] = r >= 0 ? (int)s1[r] : 0;
-                right[k] = gap + (L1 - 1 - r) * gap; // M[r][L2]
+                right[k] = FD_INF;
             }
             for (int c = 0; c < na; c++) { // T[c][lane]: only this lane ever reads its column, no synchronisation needed
                 const int b = s_alpha[c];
@@ -341,86 +433,90 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
                 Tw[c * 32] = w;
             }
         }
-        int diag0 = (r0 + 1 == L1) ? 0 : gap + (L1 - 2 - r0) * gap; // M[r0+1][L2]
-        int out_pk = 0, in_pk = 0;
+#pragma unroll
+        for (int i = 0; i < C; i++) top[i] = 0;
+        int diag0 = FD_INF;
+        uint32_t cwn[C];
+        {   // cost words of the first super-step
+            const uint32_t codes = *reinterpret_cast<const uint32_t *>(s_cc + FD_CCPAD - C * lane);
+#pragma unroll
+            for (int i = 0; i < C; i++) cwn[i] = Tw[((codes >> (8 * i)) & 0xffu) * 32];
+        }
         const bool has_producer = band > 0, has_consumer = band + 1 < nbands;
-        const unsigned in_base = has_producer ? (unsigned)((band - 1) / warps) * (unsigned)L2 : 0u;
-        const unsigned out_base = (unsigned)(band / warps) * (unsigned)L2;
+        const unsigned in_pos = has_producer ? (unsigned)((band - 1) / warps) * span : 0u;
+        const unsigned out_pos = (unsigned)(band / warps) * span;
         const bool wr_ring = has_consumer && lane == 31;
         const int rows_here = min(BAND, L1 - band * BAND); // rows of this band that exist
-        TC *tlane = tile + (size_t)(lane * R) * FD_RS;
+        const int row_top = L1 - 1 - band * BAND;          // table row of (lane 0, k 0)
 
         for (int ch = 0; ch < nchunks; ch++) {
-            const int s0 = ch * FD_CHUNK;
-            // ---- lane 0's inputs for the next FD_CHUNK steps: lane q < FD_CHUNK fetches column counter s0 + q
-            if (s0 < L2) {
-                const int kk = s0 + lane;
-                unsigned need = 0;
-                if (has_producer) {
-                    need = in_base + (unsigned)min(s0 + FD_CHUNK, L2);
+            const int u0 = ch * FD_SS;
+            const int c0 = u0 * C; // first column counter of lane 0 in this chunk
+            // ---- lane 0's row below for the chunk's 16 columns: the producer band's top row (ring) or the border row
+            const int *inp = bord;
+            if (has_producer) {
+                if (c0 < Lp) {
+                    const unsigned need = in_pos + (unsigned)min(c0 + FD_SS * C, Lp);
                     while ((int)(s_prod[pwarp] - need) < 0) { }
-                    __threadfence_block();
+                    FD_ORDER();
+                    if (lane == 0) s_cons[pwarp] = in_pos + (unsigned)c0; // everything before this chunk has been read
                 }
-                if (lane < FD_CHUNK && kk < L2) {
-                    const int code = s_code[s2[L2 - 1 - kk]];
-                    const int v = has_producer ? ring_in[(in_base + (unsigned)kk) & (FD_RING - 1)] : gap + kk * gap; // M[L1][L2-1-kk]
-                    in_pk = (v << 7) | code;
+                inp = ring_in + ((in_pos + (unsigned)c0) & (FD_RING - 1));
+            } else {
+                __syncwarp();
+                if (lane < 16) {
+                    const int j = Lp - 1 - (c0 + lane);
+                    bord[lane] = (j >= 0 && j <= L2) ? gap * (L2 - j) : FD_INF;
                 }
-                if (has_producer) {
-                    __syncwarp();
-                    if (lane == 0) s_cons[pwarp] = need;
-                }
+                __syncwarp();
             }
-            // ---- back-pressure: lane 31's next FD_CHUNK values must fit in the ring
+            // ---- back-pressure: lane 31's next 16 columns must fit in the ring
             if (has_consumer) {
-                const int k31 = s0 - 31;
-                if (k31 + FD_CHUNK > 0 && k31 < L2) {
-                    const unsigned top = out_base + (unsigned)min(k31 + FD_CHUNK, L2);
-                    while ((int)(top - s_cons[warp]) > FD_RING) { }
+                const int g31 = u0 - 31; // lane 31's first group of this chunk
+                if (g31 + FD_SS > 0 && g31 < G) {
+                    const unsigned topw = out_pos + (unsigned)min((g31 + FD_SS) * C, Lp);
+                    while ((int)(topw - s_cons[warp]) > FD_RING) { }
                 }
             }
-            TC *tcol = tlane + (s0 & (FD_TW - 1));
-            if (s0 >= 31 && s0 + FD_CHUNK - 1 < L2)
-                fd_steps<TC, R, false>(s0, lane, L2, gap, Tw, tcol, right, diag0, out_pk, in_pk, wr_ring, ring_out, out_base);
+            unsigned char *tunit = tile + (u0 & (FD_WIN - 1)) * GEO::SG + lane * GEO::UNIT;
+            const uint8_t *cc_lane = s_cc + FD_CCPAD + C * (u0 - lane);
+            if (u0 < 32)
+                fd_chunk<TC, true>(u0, lane, G, gap, Tw, cc_lane, tunit, inp, right, diag0, top, cwn, wr_ring, ring_out, out_pos);
             else
-                fd_steps<TC, R, true>(s0, lane, L2, gap, Tw, tcol, right, diag0, out_pk, in_pk, wr_ring, ring_out, out_base);
+                fd_chunk<TC, false>(u0, lane, G, gap, Tw, cc_lane, tunit, inp, right, diag0, top, cwn, wr_ring, ring_out, out_pos);
             // ---- publish the top row's progress
             if (has_consumer) {
-                __threadfence_block();
-                const int k31 = s0 + FD_CHUNK - 1 - 31;
-                if (lane == 31 && k31 >= 0) s_prod[warp] = out_base + (unsigned)min(k31 + 1, L2);
+                FD_ORDER();
+                const int g31 = u0 + FD_SS - 1 - 31; // lane 31's last finished group
+                if (lane == 31 && g31 >= 0) s_prod[warp] = out_pos + (unsigned)min((g31 + 1) * C, Lp);
             }
-            // ---- every FD_TW steps: write the staged tile out, one coalesced row segment per row.  Slot q of row
-            //      (ln, k) holds step s = w0 + q, i.e. column counter s - ln of table row top - (ln * R + k).
-            if ((s0 & (FD_TW - 1)) == FD_TW - FD_CHUNK || ch == nchunks - 1) {
+            // ---- every FD_WIN super-steps: write the staged window out.  One 4-cell vector per lane: lanes 8 kq .. 8 kq + 7
+            //      carry the window's 8 column groups of row ln * R + kq, i.e. 4 rows x 32 columns per warp instruction.
+            if ((u0 & (FD_WIN - 1)) == FD_WIN - FD_SS || ch == nchunks - 1) {
                 __syncwarp();
-                const int w0 = s0 & ~(FD_TW - 1);
-                const int s_end = s0 + FD_CHUNK - 1;
-                const int s = w0 + lane;
-                const int top = L1 - 1 - band * BAND; // table row of (ln 0, k 0)
-                const TC *trd = tile + lane;
-                TC *dst = M + (size_t)top * cols + (L2 - 1 - s);
-                if (w0 >= 31 && w0 + FD_TW - 1 < L2 && s_end >= w0 + FD_TW - 1 && rows_here == BAND) {
-#pragma unroll 4
-                    for (int ln = 0; ln < 32; ln++) {
+                const int w0 = u0 & ~(FD_WIN - 1);
+                const int u_end = u0 + FD_SS - 1;
+                const int sg = lane & 7, kq = lane >> 3;
+                const int u = w0 + sg;
+                const unsigned char *tsrc = tile + sg * GEO::SG + kq * (C * (int)sizeof(TC));
+                // group of lane ln at super-step u: g = u - ln; its lowest column j0 = Lp - 4 g - 4; table row row_top - (ln R + kq)
+                TC *dst = M + (ptrdiff_t)(row_top - kq) * pitch + (Lp - C * u - C);
+                const ptrdiff_t step = C - (ptrdiff_t)R * pitch;
+                // this lane's vectors are valid for ln in [lo, hi): its group u - ln inside the table, its row inside the band
+                const int lnmax = (rows_here - kq + R - 1) / R;
+                const int lo = max(0, u - G + 1);
+                const int hi = u <= u_end ? min(min(32, u + 1), lnmax) : 0;
+                const unsigned span_ln = (unsigned)max(hi - lo, 0);
+                using V = typename std::conditional<sizeof(TC) == 2, uint2, int4>::type;
+#pragma unroll 1
+                for (int ln0 = 0; ln0 < 32; ln0 += 8) { // 8 vectors in flight: loads first, then predicated stores (no branches)
+                    V buf[8];
 #pragma unroll
-                        for (int k = 0; k < R; k++) {
-                            dst[ln] = trd[0];
-                            dst -= cols;
-                            trd += FD_RS;
-                        }
-                    }
-                } else {
-                    int rr = 0;
-                    for (int ln = 0; ln < 32 && rr < rows_here; ln++) {
-                        const int kc = s - ln;
-                        const bool ok = s <= s_end && kc >= 0 && kc < L2;
+                    for (int q = 0; q < 8; q++) buf[q] = *reinterpret_cast<const V *>(tsrc + (ln0 + q) * GEO::UNIT);
 #pragma unroll
-                        for (int k = 0; k < R; k++, rr++) {
-                            if (ok && rr < rows_here) dst[ln] = trd[0];
-                            dst -= cols;
-                            trd += FD_RS;
-                        }
+                    for (int q = 0; q < 8; q++) {
+                        const int ln = ln0 + q;
+                        fd_store_if((unsigned)(ln - lo) < span_ln, dst + ln * step, buf[q]);
                     }
                 }
                 __syncwarp();
@@ -473,18 +569,27 @@ static int launch_pair_dp_cfg(pg_ctx *ctx, float *kernel_ms)
 // Linear-gap fast path: see pair_dp_linear_kernel.
 static int launch_pair_dp_linear(pg_ctx *ctx, float *kernel_ms)
 {
-    constexpr int MAXW = 8, R = 4;
-    int max_bands = 1;
-    for (const PairGeom &g : ctx->pairs) max_bands = std::max(max_bands, (g.rows - 1 + 32 * R - 1) / (32 * R));
-    const int warps = std::min(MAXW, max_bands);
+    constexpr int MAXW = 8;
+    int max_bands = 1, max_l2 = 1;
+    for (const PairGeom &g : ctx->pairs) {
+        max_bands = std::max(max_bands, (g.rows - 1 + 32 * FD_R - 1) / (32 * FD_R));
+        max_l2 = std::max(max_l2, g.cols - 1);
+    }
+    int warps = std::min(MAXW, max_bands);
     const int nalpha = std::max(1, ctx->n_alpha);
-    const size_t cell = ctx->dp.cell16 ? 2 : 4;
-    const size_t smem = 8112 + 96 + 96 + (size_t)warps * FD_RING * 4 + (size_t)warps * 8 + (size_t)warps * nalpha * 32 * 4 +
-                        (size_t)warps * 32 * R * FD_RS * cell + 16;
+    const int cc_bytes = (((max_l2 + 1 + FD_C - 1) & ~(FD_C - 1)) + 2 * FD_CCPAD + 15) & ~15;
+    const size_t tile = ctx->dp.cell16 ? FdGeom<uint16_t>::TILE : FdGeom<int32_t>::TILE;
+    auto smem_for = [&](int w) {
+        return (size_t)8112 + 96 + 96 + (size_t)w * FD_RING * 4 + (size_t)w * 64 + (size_t)w * 8 + 8 + (size_t)w * nalpha * 32 * 4 + (size_t)cc_bytes +
+               (size_t)w * tile + 16;
+    };
+    while (warps > 1 && smem_for(warps) > 220 * 1024) warps--; // long sequences / large alphabets: fewer bands in flight
+    const size_t smem = smem_for(warps);
+    if (smem > 227 * 1024) return -1; // does not fit: the caller runs the general kernel
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<ctx->npairs, warps * 32, smem, ctx->stream>>>(ctx->dp, warps, nalpha);
+        kern<<<ctx->npairs, warps * 32, smem, ctx->stream>>>(ctx->dp, warps, nalpha, cc_bytes);
         return cudaGetLastError();
     };
     cudaEvent_t e0, e1;
@@ -510,8 +615,10 @@ int pg_launch_pair_dp(pg_ctx *ctx, float *kernel_ms)
     // GapOpen == GapExtension (the reference's constants) and byte-sized costs: the lean linear-gap kernel.  Anything else
     // (general affine constants, costs beyond 255) runs the general kernel below.  PG_DP_KERNEL=general forces it.
     const char *force = getenv("PG_DP_KERNEL");
-    if (ctx->dp.gap_open == ctx->dp.gap_ext && ctx->cost_u8 && ctx->dp.gap_open >= 0 && !(force && force[0] == 'g'))
-        return launch_pair_dp_linear(ctx, kernel_ms);
+    if (ctx->dp.gap_open == ctx->dp.gap_ext && ctx->cost_u8 && ctx->dp.gap_open >= 0 && !(force && force[0] == 'g')) {
+        const int rc = launch_pair_dp_linear(ctx, kernel_ms);
+        if (rc >= 0) return rc; // -1: the column codes of a very long sequence do not fit in shared memory
+    }
     // measured on B200 (ms at S7 / S8): 8 rows/lane x 4 warps 0.209 / 0.421, 4 x 8 0.170 / 0.361, 2 x 16 0.190 / 0.430
     const char *e = getenv("PG_DP_CFG");
     const int cfg = e ? atoi(e) : 1;

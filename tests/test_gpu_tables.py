@@ -114,3 +114,59 @@ def test_state_errors(gpu_lib):
     g.close()
     with pytest.raises(gpu_lib.PastarError):
         gpu_lib.PastarGPU(["AC", "AC"])  # N=2 is not in max_seq_helper.h
+
+
+@pytest.mark.parametrize("lens", [(1100, 900, 40), (2200, 300, 5), (129, 128, 127), (16, 15, 17), (1, 700, 31)])
+def test_tables_long_multi_pass(gpu_lib, lens):
+    """More bands than warps (a warp takes several bands, rings wrap), 32-bit cells (30 * (L1 + L2) >= 65536) and band /
+    chunk boundary lengths, through the linear-gap kernel."""
+    seqs = [random_seqs(1, L, 300 + i)[0] for i, L in enumerate(lens)]
+    with gpu_lib.PastarGPU(seqs, weights=None) as g:
+        g.build_pair_tables()
+        k = 0
+        for i in range(len(seqs) - 1):
+            for j in range(i + 1, len(seqs)):
+                assert np.array_equal(g.pair_table(k), O.pair_table(seqs[i], seqs[j])), (lens, i, j)
+                k += 1
+
+
+def test_tables_wide_alphabet(gpu_lib):
+    """Every residue code the 90 x 90 cost table admits (Cost.h:49), not just the 20 amino acids."""
+    import random
+    r = random.Random(9)
+    seqs = ["".join(chr(r.randrange(33, 90)) for _ in range(L)) for L in (150, 140, 160)]
+    with gpu_lib.PastarGPU(seqs, weights=None) as g:
+        g.build_pair_tables()
+        k = 0
+        for i in range(2):
+            for j in range(i + 1, 3):
+                assert np.array_equal(g.pair_table(k), O.pair_table(seqs[i], seqs[j])), (i, j)
+                k += 1
+
+
+def _numpy_linear_dp(s1, s2, cost, gap):
+    L1, L2 = len(s1), len(s2)
+    M = np.zeros((L1 + 1, L2 + 1), dtype=np.int64)
+    M[L1, :] = gap * (L2 - np.arange(L2 + 1))
+    M[:, L2] = gap * (L1 - np.arange(L1 + 1))
+    for a in range(L1 - 1, -1, -1):
+        for b in range(L2 - 1, -1, -1):
+            M[a, b] = min(M[a + 1, b] + gap, M[a, b + 1] + gap, M[a + 1, b + 1] + cost[ord(s1[a]), ord(s2[b])])
+    return M.astype(np.int32)
+
+
+@pytest.mark.parametrize("scale,general", [(1, True), (20, False), (3, False)])
+def test_tables_custom_costs(gpu_lib, scale, general, monkeypatch):
+    """A caller-supplied cost table: byte-sized costs take the linear-gap kernel, larger ones (x20: up to 500) and
+    PG_DP_KERNEL=general take the general kernel; both must give the same cells as a plain DP."""
+    if general:
+        monkeypatch.setenv("PG_DP_KERNEL", "general")
+    seqs = random_seqs(3, 70, 55)
+    cost = (O.cost_table().astype(np.int32) * scale).astype(np.int32)
+    with gpu_lib.PastarGPU(seqs, weights=None, cost=cost) as g:
+        g.build_pair_tables()
+        k = 0
+        for i in range(2):
+            for j in range(i + 1, 3):
+                assert np.array_equal(g.pair_table(k), _numpy_linear_dp(seqs[i], seqs[j], cost, 30)), (scale, i, j)
+                k += 1
