@@ -265,10 +265,16 @@ __device__ __forceinline__ void fd_store_if(bool ok, void *ptr, const int4 &v)
 // or past it (g >= G) work on garbage that nothing valid ever reads - the wavefront hands a lane only blocks of the
 // group it is about to compute - so the chunk has no bounds checks and no divergence.  RAMP (the first 32 super-steps of
 // a band): a lane's running state is reset when it enters the table (g == 0).
+//
+// The sweep runs on N[i][j] = M[i][j] - gap * ((L1 - i) + (L2 - j)), the cost in excess of the all-gaps path.  Both gap
+// moves then cost nothing and the diagonal costs c - 2 gap (tabulated as such), so a cell is ONE add and ONE three-input
+// minimum,   N = min3(N_below, N_right, N_diag + c'),   and both borders are N = 0.  B200's integer pipes issue a warp
+// instruction every other cycle, so the step is bound by its instruction count: costs are tabulated as ready-to-add
+// 32-bit words (no byte extraction), M is restored when the block is staged (adj = gap * distance of its corner cell).
 template <typename TC, bool RAMP>
-__device__ __forceinline__ void fd_chunk(int u0, int lane, int G, int gap, const uint32_t *Tw, const uint8_t *cc_lane, unsigned char *tunit,
-                                         const int *inp, int (&right)[FD_R], int &diag0, int (&top)[FD_C], uint32_t (&cwn)[FD_C], bool wr_ring,
-                                         int *ring_out, unsigned out_pos)
+__device__ __forceinline__ void fd_chunk(int u0, int lane, int G, int gap, const int4 *Tw, const uint8_t *cc_lane, unsigned char *tunit,
+                                         const int *inp, int (&right)[FD_R], int &diag0, int (&top)[FD_C], int4 (&cwn)[FD_C], bool wr_ring,
+                                         int *ring_out, unsigned out_pos, int adj0)
 {
 #pragma unroll
     for (int t = 0; t < FD_SS; t++) {
@@ -277,9 +283,14 @@ __device__ __forceinline__ void fd_chunk(int u0, int lane, int G, int gap, const
         for (int i = 0; i < FD_C; i++) up[i] = __shfl_up_sync(0xffffffffu, top[i], 1);
         const int4 in4 = *reinterpret_cast<const int4 *>(inp + FD_C * t); // lane 0's row below (uniform address: broadcast)
         const int g = u0 + t - lane;                                      // my column group: columns Lp-1-4g-i, i = 0..3
-        uint32_t cw[FD_C];
+        int cw[FD_C][FD_R];
 #pragma unroll
-        for (int i = 0; i < FD_C; i++) cw[i] = cwn[i];
+        for (int i = 0; i < FD_C; i++) {
+            cw[i][0] = cwn[i].x;
+            cw[i][1] = cwn[i].y;
+            cw[i][2] = cwn[i].z;
+            cw[i][3] = cwn[i].w;
+        }
         {   // the next super-step's cost words travel while this block is computed
             const uint32_t codes = *reinterpret_cast<const uint32_t *>(cc_lane + FD_C * (t + 1));
 #pragma unroll
@@ -304,8 +315,7 @@ __device__ __forceinline__ void fd_chunk(int u0, int lane, int G, int gap, const
             prevR = r;
 #pragma unroll
             for (int i = 0; i < FD_C; i++) {
-                const int c = (int)__byte_perm(cw[i], 0u, 0x4440u | (unsigned)k);
-                const int v = __viaddmin_s32(min(prev[i], r), gap, d + c);
+                const int v = __vimin3_s32(prev[i], r, d + cw[i][k]);
                 d = prev[i];
                 prev[i] = v;
                 r = v;
@@ -315,6 +325,16 @@ __device__ __forceinline__ void fd_chunk(int u0, int lane, int G, int gap, const
         }
 #pragma unroll
         for (int i = 0; i < FD_C; i++) top[i] = prev[i];
+        {   // back to M: cell (k, i) lies k + i steps further from the corner than the block's cell (0, 0)
+            int e[FD_R + FD_C - 1];
+            e[0] = adj0 + 4 * gap * t;
+#pragma unroll
+            for (int q = 1; q < FD_R + FD_C - 1; q++) e[q] = e[q - 1] + gap;
+#pragma unroll
+            for (int k = 0; k < FD_R; k++)
+#pragma unroll
+                for (int i = 0; i < FD_C; i++) m[k][i] += e[k + i];
+        }
         // ---- stage the block: memory order is ascending column, i.e. i = 3, 2, 1, 0
         unsigned char *tu = tunit + t * FdGeom<TC>::SG;
         if constexpr (sizeof(TC) == 2) {
@@ -348,7 +368,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
     int *s_bord = s_ring + warps * FD_RING;                        // [warps][16]: band 0's row below (the border row)
     volatile unsigned *s_prod = reinterpret_cast<volatile unsigned *>(s_bord + warps * 16);
     volatile unsigned *s_cons = s_prod + warps;
-    uint32_t *s_T = const_cast<uint32_t *>(reinterpret_cast<volatile uint32_t *>(s_cons + warps)) + ((warps & 1) ? 2 : 0); // keep 16-byte alignment
+    int4 *s_T = reinterpret_cast<int4 *>(const_cast<unsigned *>(s_cons + warps) + ((warps & 1) ? 2 : 0)); // [warps][nalpha][32] x 4 rows; 16-byte aligned
     uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_T + (size_t)warps * nalpha * 32);                                          // column codes, sweep order
     unsigned char *s_tile = s_cc + cc_bytes;                                                                                  // [warps][GEO::TILE]
     __shared__ int s_na;
@@ -367,6 +387,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
     {   // cost table -> bytes (8100 = 2025 x 4 entries)
         const int4 *src = reinterpret_cast<const int4 *>(p.cost);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_cost8);
+#pragma unroll 4
         for (int i = threadIdx.x; i < 2025; i += blockDim.x) {
             const int4 v = __ldg(src + i);
             dst[i] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) | ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
@@ -403,7 +424,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nbands = (L1 + BAND - 1) / BAND;
-    uint32_t *Tw = s_T + (size_t)warp * nalpha * 32 + lane;
+    int4 *Tw = s_T + (size_t)warp * nalpha * 32 + lane;
     unsigned char *tile = s_tile + (size_t)warp * GEO::TILE;
     int *ring_out = s_ring + warp * FD_RING;
     const int pwarp = (warp + warps - 1) % warps;
@@ -425,18 +446,16 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
                 a[k] = r >= 0 ? (int)s1[r] : 0;
                 right[k] = FD_INF;
             }
-            for (int c = 0; c < na; c++) { // T[c][lane]: only this lane ever reads its column, no synchronisation needed
-                const int b = s_alpha[c];
-                uint32_t w = 0;
-#pragma unroll
-                for (int k = 0; k < R; k++) w |= (uint32_t)s_cost8[a[k] * 90 + b] << (8 * k);
-                Tw[c * 32] = w;
+            for (int c = 0; c < na; c++) { // T[c][lane] = cost - 2 gap of the lane's 4 rows against residue code c.  Only this
+                const int b = s_alpha[c];  // lane ever reads its column: no synchronisation needed
+                Tw[c * 32] = make_int4((int)s_cost8[a[0] * 90 + b] - 2 * gap, (int)s_cost8[a[1] * 90 + b] - 2 * gap, (int)s_cost8[a[2] * 90 + b] - 2 * gap,
+                                       (int)s_cost8[a[3] * 90 + b] - 2 * gap);
             }
         }
 #pragma unroll
         for (int i = 0; i < C; i++) top[i] = 0;
         int diag0 = FD_INF;
-        uint32_t cwn[C];
+        int4 cwn[C];
         {   // cost words of the first super-step
             const uint32_t codes = *reinterpret_cast<const uint32_t *>(s_cc + FD_CCPAD - C * lane);
 #pragma unroll
@@ -466,7 +485,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
                 __syncwarp();
                 if (lane < 16) {
                     const int j = Lp - 1 - (c0 + lane);
-                    bord[lane] = (j >= 0 && j <= L2) ? gap * (L2 - j) : FD_INF;
+                    bord[lane] = (j >= 0 && j <= L2) ? 0 : FD_INF; // N = 0 on the border row
                 }
                 __syncwarp();
             }
@@ -480,10 +499,13 @@ __global__ void __launch_bounds__(32 * MAXW, 1) pair_dp_linear_kernel(const __gr
             }
             unsigned char *tunit = tile + (u0 & (FD_WIN - 1)) * GEO::SG + lane * GEO::UNIT;
             const uint8_t *cc_lane = s_cc + FD_CCPAD + C * (u0 - lane);
+            // gap * distance from the corner (L1, L2) of this lane's cell (k 0, i 0) at the chunk's first super-step:
+            // row r0, column Lp - 1 - 4 (u0 - lane)
+            const int adj0 = gap * ((L1 - r0) + (L2 - (Lp - 1 - C * (u0 - lane))));
             if (u0 < 32)
-                fd_chunk<TC, true>(u0, lane, G, gap, Tw, cc_lane, tunit, inp, right, diag0, top, cwn, wr_ring, ring_out, out_pos);
+                fd_chunk<TC, true>(u0, lane, G, gap, Tw, cc_lane, tunit, inp, right, diag0, top, cwn, wr_ring, ring_out, out_pos, adj0);
             else
-                fd_chunk<TC, false>(u0, lane, G, gap, Tw, cc_lane, tunit, inp, right, diag0, top, cwn, wr_ring, ring_out, out_pos);
+                fd_chunk<TC, false>(u0, lane, G, gap, Tw, cc_lane, tunit, inp, right, diag0, top, cwn, wr_ring, ring_out, out_pos, adj0);
             // ---- publish the top row's progress
             if (has_consumer) {
                 FD_ORDER();
@@ -580,7 +602,7 @@ static int launch_pair_dp_linear(pg_ctx *ctx, float *kernel_ms)
     const int cc_bytes = (((max_l2 + 1 + FD_C - 1) & ~(FD_C - 1)) + 2 * FD_CCPAD + 15) & ~15;
     const size_t tile = ctx->dp.cell16 ? FdGeom<uint16_t>::TILE : FdGeom<int32_t>::TILE;
     auto smem_for = [&](int w) {
-        return (size_t)8112 + 96 + 96 + (size_t)w * FD_RING * 4 + (size_t)w * 64 + (size_t)w * 8 + 8 + (size_t)w * nalpha * 32 * 4 + (size_t)cc_bytes +
+        return (size_t)8112 + 96 + 96 + (size_t)w * FD_RING * 4 + (size_t)w * 64 + (size_t)w * 8 + 8 + (size_t)w * nalpha * 32 * 16 + (size_t)cc_bytes +
                (size_t)w * tile + 16;
     };
     while (warps > 1 && smem_for(warps) > 220 * 1024) warps--; // long sequences / large alphabets: fewer bands in flight
