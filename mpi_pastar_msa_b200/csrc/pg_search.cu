@@ -9,13 +9,18 @@
 //   sender / receiver / decoder  pastar/pastar_functions/*.cpp          successor exchange between partitions
 //
 // Data layout in HBM (all device resident, nothing per-node on the host):
-//   table   open-addressing hash table, one entry per coordinate ever generated:
-//             KEYW=1: {u64 key+1, u64 val}            16 B (eight per 128 B line)
-//             KEYW=2: {u64 key.lo, u64 key.hi|1<<63, u64 val, pad} 32 B
-//           key = coordinates packed key_bits each; val = ~(g<<32 | open<<31 | parenti)
-//           so a zeroed table is empty and "no g yet".  This is ClosedList and the
-//           pos-index of OpenList in one structure: best g per coordinate.  The placement
-//           (home_slot) keeps the successors of one parent in shared 128-byte lines.
+//   table   ClosedList and the pos-index of OpenList in one structure: best g per coordinate.
+//           The lattice is cut into aligned 2^D cubes (D = min(N, 7): the lowest bit of the first D
+//           coordinates); a cube is one BLOCK of 2^D values, direct-mapped by those bits, so a value
+//           needs no key of its own:
+//             directory  open addressing over block keys (the packed key with those D bits cleared):
+//                        KEYW=1 {u64 blockkey+1}, KEYW=2 {u64 lo, u64 hi|1<<63}; 0 = free.  Sixteen
+//                        (eight) neighbouring blocks share a 128-byte directory line.
+//             values     block s is values[s * 2^D ..]; VALW=4: ~(g << (N+1) | open << N | parenti) when
+//                        that fits 32 bits, else VALW=8: ~(g<<32 | open<<31 | parenti); 0 = empty.
+//           A successor probe reads one (L1/L2-resident) directory word and one 4-byte value: the 127
+//           successors of a node touch about 30 lines of HBM instead of 54 with 16-byte keyed entries
+//           (tools/microbench3.cu: a random line costs the same whatever is read from it, 36.6 G/s).
 //   buckets one u64 per f value {chunk offset, log2 size, fill}: the priority index of
 //           OpenList.  A bucket is a backward-linked list of chunks of u32 table slots
 //           whose sizes double (64, 128, ... 256 Ki entries), so a bucket of any size
@@ -63,9 +68,14 @@ struct PlanEntry {
 } // namespace
 
 struct SearchState {
-    int keyw = 1;
-    uint64_t cap = 0;        // slots (power of two)
-    uint64_t *d_table = nullptr;
+    int keyw = 1;            // u64 words per packed key
+    int valw = 8;            // bytes per value (4 when g, the open bit and the move mask fit 32 bits)
+    int D = 0, DL = 0;       // block dimensions, directory-line dimensions
+    int nb = 31, gs = 32;    // value layout: open bit, g shift
+    uint64_t cap = 0;        // value slots = dir_slots << D (power of two)
+    uint64_t dir_slots = 0;  // directory slots = blocks (power of two)
+    unsigned long long *d_dir = nullptr;
+    void *d_vals = nullptr;
     unsigned long long *d_buckets = nullptr;
     uint32_t *d_tail = nullptr;              // per bucket: entries in the chunks behind the head
     uint32_t *d_hint = nullptr;
@@ -176,38 +186,25 @@ struct Key<2> {
 
 
 // ---------------------------------------------------------------------------------------------
-// Table placement.  A random 16-byte probe costs a whole 128-byte line of HBM traffic (measured: 36.5 G random lines/s
-// however many of a line's 8 entries are read, tools/microbench2.cu), so the table is laid out so that the successors of
-// one parent share lines: the home LINE is hashed from the key with the lowest bit of its first LB coordinates
-// cleared, and those LB bits select the entry inside the line (LB = 3: 8 x 16 B entries; LB = 2: 4 x 32 B).  The
-// 2^LB successors that differ only in whether those coordinates advance land in one line when the parent's coordinates
-// are even (1.5^LB lines on average instead of 2^LB), and neighbouring parents share lines too.  Collisions probe the
-// same entry position of the following lines (stride 2^LB slots), so the layout is kept.
+// Table: block directory + direct-mapped value blocks.  A random access costs a whole 128-byte line of HBM whatever
+// is read from it (36.6 G random lines/s, tools/microbench2/3.cu), so the layout minimises LINES per probe:
+//   * values carry no key: the 2^D coordinates that differ only in the lowest bit of the first D coordinates form a
+//     block, and a value's place inside its block is given by those D bits.  With 4-byte values a line holds a
+//     5-dimensional sub-cube: the successors of a node touch 4 * 1.5^5 = 30 lines on average;
+//   * the block's key is looked up in a directory that is 64 (128) times smaller than the values; neighbouring blocks
+//     (lowest bit of the first four block coordinates) share a directory line, so the directory lines a frontier needs
+//     stay L2 resident and a node's successors read 8 of them on average (most of them L1 hits inside a parent group).
 // ---------------------------------------------------------------------------------------------
-template <int KEYW>
-__device__ __forceinline__ unsigned long long home_slot(const Key<KEYW> &key, int kb, unsigned long long cap_mask)
-{
-    constexpr int LB = KEYW == 1 ? 3 : 2;
-    unsigned long long low = 0, clr = 0;
-#pragma unroll
-    for (int i = 0; i < LB; i++) {
-        low |= ((key.lo >> (i * kb)) & 1ull) << i; // LB * kb < 64 always (kb <= 16)
-        clr |= 1ull << (i * kb);
-    }
-    Key<KEYW> blk = key;
-    blk.lo &= ~clr;
-    return ((blk.hash() << LB) | low) & cap_mask;
-}
-template <int KEYW>
-__device__ __forceinline__ unsigned long long next_slot(unsigned long long slot, unsigned long long cap_mask)
-{
-    return (slot + (KEYW == 1 ? 8ull : 4ull)) & cap_mask;
-}
-
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p)
 {
     unsigned long long v;
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_cg_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void ld_cg_v2(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
@@ -226,9 +223,15 @@ __device__ __forceinline__ void cas128(unsigned long long *addr, unsigned long l
 }
 
 struct DevSearch {
-    unsigned long long *table;
-    unsigned long long cap_mask;
-    int kb; // bits per coordinate in the packed key
+    unsigned long long *dir;      // block directory: KEYW u64 per slot
+    unsigned long long dir_mask;  // directory slots - 1 (power of two)
+    void *vals;                   // value blocks: (dir_mask + 1) << D values of VALW bytes
+    int kb;                       // bits per coordinate in the packed key
+    int D;                        // block dimensions: lowest bit of the first D coordinates
+    int DL;                       // directory-line dimensions: lowest bit of the first DL BLOCK coordinates
+    int nb, gs;                   // value layout: open bit position, g shift (VALW=4: N, N+1; VALW=8: 31, 32)
+    unsigned long long low_lo, low_hi;   // key bits that index inside a block
+    unsigned long long line_lo, line_hi; // low bits + the bits that index inside a directory line
     unsigned long long *buckets;
     uint32_t *tail;
     uint32_t *hint; // per bucket: log2 units of the largest chunk it ever had
@@ -258,63 +261,152 @@ struct Counters { // per thread, flushed once per kernel
     unsigned expansions, generated, reopen, inserted, pushed, pruned, stale;
 };
 
-// Find / claim the table slot of a key.  Returns the slot (entry index) or ~0 when the table is full.
-// Stored key words: KEYW=1 {lo + 1}; KEYW=2 {lo, hi | 1<<63} (n*key_bits <= 127), so 0 means empty.
-template <int KEYW>
-__device__ __forceinline__ unsigned long long table_slot(const DevSearch &d, const Key<KEYW> &key, unsigned long long &val, bool &fresh)
+// ---- values.  Stored inverted, so zeroed memory is "empty, no g yet" (g reads as the largest representable).
+template <int VALW>
+struct ValT;
+template <>
+struct ValT<4> {
+    typedef unsigned T;
+};
+template <>
+struct ValT<8> {
+    typedef unsigned long long T;
+};
+template <int VALW>
+__device__ __forceinline__ typename ValT<VALW>::T val_pack(const DevSearch &d, unsigned g, unsigned mask) // an OPEN entry
 {
-    constexpr int ES = KEYW == 1 ? 2 : 4;
-    unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
-    fresh = false;
-    for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
-        unsigned long long *e = d.table + slot * ES;
+    typedef typename ValT<VALW>::T T;
+    return (T) ~(((T)g << d.gs) | ((T)1 << d.nb) | (T)mask);
+}
+template <int VALW>
+__device__ __forceinline__ unsigned val_g(const DevSearch &d, typename ValT<VALW>::T s) // empty: larger than any real g
+{
+    typedef typename ValT<VALW>::T T;
+    return (unsigned)((T)(~s) >> d.gs);
+}
+template <int VALW>
+__device__ __forceinline__ bool val_closed(const DevSearch &d, typename ValT<VALW>::T s) // s != 0
+{
+    return (s >> d.nb) & 1;
+}
+template <int VALW>
+__device__ __forceinline__ unsigned val_mask(const DevSearch &d, typename ValT<VALW>::T s)
+{
+    typedef typename ValT<VALW>::T T;
+    return (unsigned)((T)(~s) & (((T)1 << d.nb) - 1));
+}
+// the live-parent / record form of a value: g << 32 | open << 31 | parenti
+template <int VALW>
+__device__ __forceinline__ unsigned long long val_record(const DevSearch &d, typename ValT<VALW>::T s, bool open)
+{
+    return ((unsigned long long)val_g<VALW>(d, s) << 32) | (open ? OPEN_BIT : 0ull) | (unsigned long long)val_mask<VALW>(d, s);
+}
+template <int VALW>
+__device__ __forceinline__ typename ValT<VALW>::T *val_ptr(const DevSearch &d, unsigned long long slot)
+{
+    return reinterpret_cast<typename ValT<VALW>::T *>(d.vals) + slot;
+}
+template <int VALW>
+__device__ __forceinline__ typename ValT<VALW>::T ld_val(const typename ValT<VALW>::T *p)
+{
+    if constexpr (VALW == 4)
+        return ld_cg_u32(p);
+    else
+        return ld_cg_u64(p);
+}
+
+// ---- keys -> block key, place inside the block, directory slot
+template <int KEYW>
+__device__ __forceinline__ Key<KEYW> block_key(const DevSearch &d, const Key<KEYW> &key)
+{
+    Key<KEYW> b = key;
+    b.lo &= ~d.low_lo;
+    if constexpr (KEYW == 2) b.hi &= ~d.low_hi;
+    return b;
+}
+// index of `key` inside its block: the lowest bit of the first D coordinates
+template <int KEYW>
+__device__ __forceinline__ unsigned block_index(const DevSearch &d, const Key<KEYW> &key)
+{
+    unsigned idx = 0;
+    for (int i = 0; i < d.D; i++) idx |= key.field(i * d.kb, 1u) << i;
+    return idx;
+}
+// the key of entry `idx` of the block `bkey`
+template <int KEYW>
+__device__ __forceinline__ Key<KEYW> block_entry_key(const DevSearch &d, Key<KEYW> bkey, unsigned idx)
+{
+    for (int i = 0; i < d.D; i++)
+        if ((idx >> i) & 1u) bkey.add_bit(i * d.kb);
+    return bkey;
+}
+// place of a block inside its directory line: the lowest bit of the first DL block coordinates (bit 1 of the coordinates)
+template <int KEYW>
+__device__ __forceinline__ unsigned dir_pos(const DevSearch &d, const Key<KEYW> &key)
+{
+    unsigned idx = 0;
+    for (int i = 0; i < d.DL; i++) idx |= key.field(i * d.kb + 1, 1u) << i;
+    return idx;
+}
+template <int KEYW>
+constexpr int DIR_LB = KEYW == 1 ? 4 : 3; // log2 directory slots per 128-byte line
+// home directory slot of the block that holds `key`; dpos = dir_pos(key)
+template <int KEYW>
+__device__ __forceinline__ unsigned long long dir_home(const DevSearch &d, const Key<KEYW> &key, unsigned dpos)
+{
+    Key<KEYW> lk = key;
+    lk.lo &= ~d.line_lo;
+    if constexpr (KEYW == 2) lk.hi &= ~d.line_hi;
+    return ((lk.hash() << DIR_LB<KEYW>) | dpos) & d.dir_mask;
+}
+template <int KEYW>
+__device__ __forceinline__ unsigned long long dir_next(const DevSearch &d, unsigned long long dslot)
+{
+    return (dslot + (1ull << DIR_LB<KEYW>)) & d.dir_mask;
+}
+template <int KEYW>
+__device__ __forceinline__ bool dir_is(const unsigned long long h0, const unsigned long long h1, const Key<KEYW> &bkey)
+{
+    if constexpr (KEYW == 1)
+        return h0 == bkey.lo + 1;
+    else
+        return h0 == bkey.lo && h1 == (bkey.hi | (1ull << 63));
+}
+
+// Find the directory slot of the block `bkey`, starting at `dslot`; claim a free slot when `claim`.  Returns the slot
+// or ~0 (absent when !claim, directory full when claim).
+template <int KEYW>
+__device__ __forceinline__ unsigned long long dir_find(const DevSearch &d, const Key<KEYW> &bkey, unsigned long long dslot, bool claim)
+{
+    for (int probe = 0; probe < MAX_PROBE; probe++, dslot = dir_next<KEYW>(d, dslot)) {
+        unsigned long long *e = d.dir + dslot * KEYW;
+        unsigned long long h0, h1 = 0;
+        if constexpr (KEYW == 1)
+            h0 = ld_cg_u64(e);
+        else
+            ld_cg_v2(e, h0, h1);
+        if (dir_is<KEYW>(h0, h1, bkey)) return dslot;
+        if (h0 != 0 || h1 != 0) continue;
+        if (!claim) return ~0ull;
         if constexpr (KEYW == 1) {
-            unsigned long long k, v;
-            ld_cg_v2(e, k, v);
-            if (k == key.lo + 1) {
-                val = v;
-                return slot;
-            }
-            if (k != 0) continue;
-            unsigned long long prev = atomicCAS(e, 0ull, key.lo + 1);
-            if (prev == 0) {
-                fresh = true;
-                val = 0;
-                return slot;
-            }
-            if (prev == key.lo + 1) {
-                val = ld_cg_u64(e + 1);
-                return slot;
-            }
+            const unsigned long long prev = atomicCAS(e, 0ull, bkey.lo + 1);
+            if (prev == 0 || prev == bkey.lo + 1) return dslot;
         } else {
-            unsigned long long k0, k1;
-            ld_cg_v2(e, k0, k1);
-            const unsigned long long want0 = key.lo, want1 = key.hi | (1ull << 63);
-            if (k0 == want0 && k1 == want1) {
-                val = ld_cg_u64(e + 2);
-                return slot;
-            }
-            if (k0 != 0 || k1 != 0) continue;
             unsigned long long p0, p1;
-            cas128(e, want0, want1, p0, p1);
-            if (p0 == 0 && p1 == 0) {
-                fresh = true;
-                val = 0;
-                return slot;
-            }
-            if (p0 == want0 && p1 == want1) {
-                val = ld_cg_u64(e + 2);
-                return slot;
-            }
+            cas128(e, bkey.lo, bkey.hi | (1ull << 63), p0, p1);
+            if ((p0 == 0 && p1 == 0) || dir_is<KEYW>(p0, p1, bkey)) return dslot;
         }
     }
     return ~0ull;
 }
-
+// value slot (index into d.vals) of `key`, or ~0
 template <int KEYW>
-__device__ __forceinline__ unsigned long long *val_ptr(const DevSearch &d, unsigned long long slot)
+__device__ __forceinline__ unsigned long long table_find(const DevSearch &d, const Key<KEYW> &key, bool claim)
 {
-    return d.table + slot * (KEYW == 1 ? 2 : 4) + (KEYW == 1 ? 1 : 2);
+    const Key<KEYW> bkey = block_key<KEYW>(d, key);
+    const unsigned long long dslot = dir_find<KEYW>(d, bkey, dir_home<KEYW>(d, key, dir_pos<KEYW>(d, key)), claim);
+    if (dslot == ~0ull) return ~0ull;
+    return (dslot << d.D) | block_index<KEYW>(d, key);
 }
 
 // Push a table slot on the open bucket of f.  One atomicAdd hands out a position:
@@ -564,78 +656,33 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, lon
     }
 }
 
-// One record at a time: find/claim its slot starting at `slot`, install g if strictly better, push.
-// Returns UPS_* flags.
+// One record at a time: find / claim the block of `key` starting at directory slot `dslot`, install g if strictly
+// better, push.  Returns UPS_* flags.
 enum { UPS_INSERTED = 1, UPS_PUSHED = 2, UPS_REOPEN = 4 };
-template <int KEYW>
-__device__ __noinline__ unsigned upsert_from(const DevSearch &d, const Key<KEYW> key, unsigned long long slot, int gnew, int f, int mask)
+template <int KEYW, int VALW>
+__device__ __noinline__ unsigned upsert_from(const DevSearch &d, const Key<KEYW> key, unsigned long long dslot, int gnew, int f, int mask)
 {
+    typedef typename ValT<VALW>::T T;
     unsigned flags = 0;
-    constexpr int ES = KEYW == 1 ? 2 : 4;
-    unsigned long long val = 0;
-    bool found = false;
-    for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
-        unsigned long long *e = d.table + slot * ES;
-        if constexpr (KEYW == 1) {
-            unsigned long long k, v;
-            ld_cg_v2(e, k, v);
-            if (k == key.lo + 1) {
-                val = v;
-                found = true;
-                break;
-            }
-            if (k != 0) continue;
-            const unsigned long long prev = atomicCAS(e, 0ull, key.lo + 1);
-            if (prev == 0) {
-                flags |= UPS_INSERTED;
-                val = 0;
-                found = true;
-                break;
-            }
-            if (prev == key.lo + 1) {
-                val = ld_cg_u64(e + 1);
-                found = true;
-                break;
-            }
-        } else {
-            unsigned long long k0, k1;
-            ld_cg_v2(e, k0, k1);
-            const unsigned long long want0 = key.lo, want1 = key.hi | (1ull << 63);
-            if (k0 == want0 && k1 == want1) {
-                val = ld_cg_u64(e + 2);
-                found = true;
-                break;
-            }
-            if (k0 != 0 || k1 != 0) continue;
-            unsigned long long p0, p1;
-            cas128(e, want0, want1, p0, p1);
-            if (p0 == 0 && p1 == 0) {
-                flags |= UPS_INSERTED;
-                val = 0;
-                found = true;
-                break;
-            }
-            if (p0 == want0 && p1 == want1) {
-                val = ld_cg_u64(e + 2);
-                found = true;
-                break;
-            }
-        }
-    }
-    if (!found) {
+    dslot = dir_find<KEYW>(d, block_key<KEYW>(d, key), dslot, true);
+    if (dslot == ~0ull) {
         d.ctrl->error = 1;
         return flags;
     }
-    unsigned long long *vp = val_ptr<KEYW>(d, slot);
-    const unsigned long long mine = ~(((unsigned long long)(unsigned)gnew << 32) | OPEN_BIT | (unsigned long long)(unsigned)mask);
+    const unsigned long long slot = (dslot << d.D) | block_index<KEYW>(d, key);
+    T *vp = val_ptr<VALW>(d, slot);
+    T val = ld_val<VALW>(vp);
+    const T mine = val_pack<VALW>(d, (unsigned)gnew, (unsigned)mask);
     for (;;) {
-        const unsigned g_old = (unsigned)((~val) >> 32); // 0xffffffff for a fresh entry
-        if ((unsigned)gnew >= g_old) return flags;       // PAStar.cpp:228 / PriorityList.h:109: not better, drop
-        const unsigned long long prev = atomicCAS(vp, val, mine);
+        if ((unsigned)gnew >= val_g<VALW>(d, val)) return flags; // PAStar.cpp:228 / PriorityList.h:109: not better, drop
+        const T prev = atomicCAS(vp, val, mine);
         if (prev == val) break;
         val = prev;
     }
-    if (val != 0 && !((~val) & OPEN_BIT)) flags |= UPS_REOPEN; // was closed with a worse g: PAStar.cpp:230-231
+    if (val == 0)
+        flags |= UPS_INSERTED;
+    else if (val_closed<VALW>(d, val))
+        flags |= UPS_REOPEN; // was closed with a worse g: PAStar.cpp:230-231
     bucket_push(d, f, (uint32_t)slot);
     return flags | UPS_PUSHED;
 }
@@ -735,9 +782,10 @@ constexpr unsigned long long HINT_FLAG = 1ull << 31; // record word KEYW+1: {sta
 constexpr int RING_CAP = 64;                         // survivor ring, items per warp
 constexpr int PLAN_SM = 2048;
 
-template <int KEYW>
+template <int KEYW, int VALW>
 __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevSearch d)
 {
+    typedef typename ValT<VALW>::T T;
     constexpr int PF = 4; // pops per thread, each step of their dependent chains (plan -> pool -> table) issued for all four
     __shared__ uint32_t s_plan[PLAN_SM];
     __shared__ int s_wtot[8];
@@ -758,7 +806,8 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
     for (int base = blockIdx.x * 256 * PF; base < batch_n; base += gridDim.x * 256 * PF) {
         int bi[PF], pl[PF];
         uint32_t slot[PF];
-        unsigned long long old[PF], klo[PF], khi[PF];
+        T old[PF];
+        unsigned long long klo[PF], khi[PF];
 #pragma unroll
         for (int j = 0; j < PF; j++) {
             bi[j] = base + j * 256 + threadIdx.x;
@@ -785,13 +834,13 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
         }
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            old[j] = OPEN_BIT;
+            old[j] = (T)1 << d.nb; // "already closed": not live
             klo[j] = khi[j] = 0;
             if (bi[j] < batch_n) {
-                unsigned long long *e = d.table + (size_t)slot[j] * (KEYW == 1 ? 2 : 4);
-                // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion.  The key words
-                // never change once an entry exists, so they are read alongside.
-                old[j] = atomicOr(e + (KEYW == 1 ? 1 : 2), OPEN_BIT);
+                // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion.  The block's key
+                // never changes once the block exists, so it is read alongside.
+                old[j] = atomicOr(val_ptr<VALW>(d, slot[j]), (T)1 << d.nb);
+                const unsigned long long *e = d.dir + (size_t)(slot[j] >> d.D) * KEYW;
                 klo[j] = ld_cg_u64(e);
                 if constexpr (KEYW == 2) khi[j] = ld_cg_u64(e + 1);
             }
@@ -802,7 +851,7 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
         int wtot = 0;
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            bal[j] = __ballot_sync(0xffffffffu, !(old[j] & OPEN_BIT));
+            bal[j] = __ballot_sync(0xffffffffu, !val_closed<VALW>(d, old[j]));
             wtot += __popc(bal[j]);
         }
         if (lane == 0) s_wtot[threadIdx.x >> 5] = wtot;
@@ -821,11 +870,15 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
         __syncthreads(); // s_wtot / s_base are rewritten by the next sweep
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            if (!(old[j] & OPEN_BIT)) {
+            if (!val_closed<VALW>(d, old[j])) {
+                Key<KEYW> bkey;
+                bkey.lo = KEYW == 1 ? klo[j] - 1 : klo[j];
+                if constexpr (KEYW == 2) bkey.hi = khi[j] & ~(1ull << 63);
+                const Key<KEYW> key = block_entry_key<KEYW>(d, bkey, slot[j] & ((1u << d.D) - 1u));
                 unsigned long long *r = d.live + (size_t)(wbase + __popc(bal[j] & lt));
-                r[0] = KEYW == 1 ? klo[j] - 1 : klo[j];
-                if constexpr (KEYW == 2) r[d.live_cap] = khi[j] & ~(1ull << 63);
-                r[KEYW * d.live_cap] = ~old[j];
+                r[0] = key.lo;
+                if constexpr (KEYW == 2) r[d.live_cap] = key.hi;
+                r[KEYW * d.live_cap] = val_record<VALW>(d, old[j], true);
             }
             wbase += __popc(bal[j]);
         }
@@ -946,12 +999,13 @@ __device__ __forceinline__ void ring_flush(const DevSearch &d, const unsigned lo
 #ifndef PG_EXPAND_CTAS
 #define PG_EXPAND_CTAS 3 // resident CTAs per SM the expand kernel is compiled for (register budget 65536 / 256 / this)
 #endif
-template <int N, int KEYW, int MODE>
+template <int N, int KEYW, int VALW, int MODE>
 __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
                                                               const __grid_constant__ OwnerArgs oa, const __grid_constant__ ParentSrc ps)
 {
     constexpr bool MULTI = MODE != 0;   // owners are computed
     constexpr bool SEND = MODE == 1;    // ... and records sent
+    typedef typename ValT<VALW>::T T;
     using C = ExpCfg<N>;
     constexpr int XW = KEYW == 1 ? 3 : 4;
     constexpr int GROUPS = 256 / C::LP;
@@ -1087,18 +1141,29 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
         for (int i = 0; i < C::A; i++)
             if ((sub >> i) & 1) klow.add_bit(i * p.key_bits);
         const bool interior = L.alive == full;
+        // A successor's place inside its block is the parent's low bits XOR the move mask (adding 1 flips the lowest
+        // bit); a block coordinate moves on where the parent's low bit is set and the sequence advances.
+        unsigned plow = 0, pdir = 0;
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                if (i < d.D) plow |= (unsigned)(pos[i] & 1) << i;
+                if (i < d.DL) pdir |= (unsigned)((pos[i] >> 1) & 1) << i;
+            }
+        }
+        const unsigned bem = (1u << d.D) - 1u, dlm = (1u << d.DL) - 1u;
 
         for (int u = 0; u < (1 << C::UB); u++) {
             int vg[NI], vh[NI];
             pg_expand_block<N>(L, u, vg, vh);
 #pragma unroll
             for (int cb = 0; cb < NI; cb += PF) {
-                unsigned long long lk[PF], lv[PF];
-                unsigned long long lw[KEYW == 2 ? PF : 1]; // KEYW=2: the value word
-                uint32_t ls[PF];
+                unsigned long long h0[PF], h1[KEYW == 2 ? PF : 1]; // directory words
+                T lv[PF];                                            // values
+                uint32_t ls[PF];                                     // directory slots
                 int lg[PF];
                 unsigned vmask = 0;
-                // ---- pass 1: issue the probes
+                // ---- pass 1a: f, pruning, owner; ISSUE the directory loads (L1 / L2: neighbouring successors share words)
 #pragma unroll
                 for (int j = 0; j < PF; j++) {
                     const int i = cb + j;
@@ -1107,7 +1172,9 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     bool v = act && mask != 0 && (interior || !(mask & ~L.alive));
                     bool rem = false;
                     int rown = 0;
-                    lk[j] = lv[j] = 0;
+                    h0[j] = 0;
+                    if constexpr (KEYW == 2) h1[j] = 0;
+                    lv[j] = 0;
                     ls[j] = 0;
                     lg[j] = 0;
                     int own = d.part;
@@ -1151,7 +1218,6 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                         lg[j] = gn;
                     }
                     if (v) {
-                        const Key<KEYW> key = klow.plus(s_keyhigh[high]);
                         if constexpr (SEND) {
                             if (own != d.part) { // remote successor: goes to the owner's outbox below
                                 rem = true;
@@ -1160,11 +1226,18 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                             }
                         }
                         if (v) {
-                            const unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
-                            ls[j] = (uint32_t)slot;
-                            const unsigned long long *e = d.table + slot * (KEYW == 1 ? 2 : 4);
-                            ld_cg_v2(e, lk[j], lv[j]); // KEYW=2: 32 B entry {k0, k1, val, pad}
-                            if constexpr (KEYW == 2) lw[j] = ld_cg_u64(e + 2);
+                            const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                            const unsigned dpos = (pdir ^ (plow & (unsigned)mask)) & dlm;
+                            const unsigned long long dslot = dir_home<KEYW>(d, key, dpos);
+                            ls[j] = (uint32_t)dslot;
+                            const unsigned long long *e = d.dir + dslot * KEYW;
+                            if constexpr (KEYW == 1) {
+                                h0[j] = __ldg(e);
+                            } else {
+                                const ulonglong2 hh = __ldg(reinterpret_cast<const ulonglong2 *>(e));
+                                h0[j] = hh.x;
+                                h1[j] = hh.y;
+                            }
                             vmask |= 1u << j;
                         }
                     }
@@ -1190,6 +1263,26 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                         }
                     }
                 }
+                // ---- pass 1b: where the directory word is this successor's block, ISSUE the 4 / 8-byte value load.  No
+                //      block there (free slot: nothing of this cube exists yet) or another block's key (collision): the
+                //      successor goes to the insert kernel, which walks the directory.
+                unsigned hmask = 0;
+#pragma unroll
+                for (int j = 0; j < PF; j++) {
+                    if ((vmask >> j) & 1u) {
+                        const int i = cb + j;
+                        const int high = (u << C::IB) | i;
+                        const int mask = (high << C::A) | sub;
+                        const Key<KEYW> bkey = block_key<KEYW>(d, klow.plus(s_keyhigh[high]));
+                        unsigned long long w1 = 0;
+                        if constexpr (KEYW == 2) w1 = h1[j];
+                        if (dir_is<KEYW>(h0[j], w1, bkey)) {
+                            const unsigned idx = (plow ^ (unsigned)mask) & bem;
+                            lv[j] = ld_val<VALW>(val_ptr<VALW>(d, ((unsigned long long)ls[j] << d.D) | idx));
+                            hmask |= 1u << j;
+                        }
+                    }
+                }
                 PH_MARK(3); // pass 1: issue probes (+ remote appends)
                 // ---- pass 2: compare; stage the survivors
 #pragma unroll
@@ -1198,27 +1291,11 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     const int high = (u << C::IB) | i;
                     const int mask = (high << C::A) | sub;
                     bool slow = false;
-                    unsigned long long start = ls[j];
                     Key<KEYW> key = Key<KEYW>::zero();
                     if ((vmask >> j) & 1u) {
                         key = klow.plus(s_keyhigh[high]);
-                        if constexpr (KEYW == 1) {
-                            if (lk[j] == key.lo + 1) {
-                                const unsigned g_old = (unsigned)((~lv[j]) >> 32);
-                                slow = (unsigned)lg[j] < g_old; // better g
-                            } else {
-                                slow = true; // empty slot or collision
-                                if (lk[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
-                            }
-                        } else {
-                            if (lk[j] == key.lo && lv[j] == (key.hi | (1ull << 63))) {
-                                const unsigned g_old = (unsigned)((~lw[j]) >> 32);
-                                slow = (unsigned)lg[j] < g_old;
-                            } else {
-                                slow = true;
-                                if (lk[j] != 0 || lv[j] != 0) start = next_slot<KEYW>(start, d.cap_mask);
-                            }
-                        }
+                        // same coordinate, g not better (PAStar.cpp:228 / PriorityList.h:109) ends here: the common case
+                        slow = !((hmask >> j) & 1u) || (unsigned)lg[j] < val_g<VALW>(d, lv[j]);
                     }
                     const unsigned sb = __ballot_sync(0xffffffffu, slow);
                     if (sb) {
@@ -1227,7 +1304,8 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                             q[0] = key.lo;
                             if constexpr (KEYW == 2) q[1] = key.hi;
                             q[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)(lg[j] + vh[i] + s_hhh[high]);
-                            q[KEYW + 1] = (start << 32) | HINT_FLAG | (unsigned long long)(unsigned)mask;
+                            // the directory slot is a hint for the insert kernel when this successor's block was found there
+                            q[KEYW + 1] = ((unsigned long long)ls[j] << 32) | (((hmask >> j) & 1u) ? HINT_FLAG : 0ull) | (unsigned long long)(unsigned)mask;
                         }
                         qtail += __popc(sb);
                         __syncwarp();
@@ -1281,18 +1359,19 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
 // Dedupe + push of successor records: the round's local survivors and the records received from other partitions
 // (PAStar.cpp:240-250 consume_queue -> enqueue; PAStar.cpp:219-237; PriorityList.h:104-113).  The record count is read
 // from device memory, so a driver can chain rounds without a host round trip.  Every step of the chain
-//     record -> table entry -> CAS key (new coordinate) -> CAS value (strictly better g) -> bucket atomicAdd -> pool store
+//     record -> directory word (-> claim a free slot for a new block) -> value -> CAS value (strictly better g)
+//            -> bucket atomicAdd -> pool store
 // is issued for 4 records per thread before any of its results is used, so 4 dependent chains overlap per thread.
-// What does not fit the straight line (hash collision, a CAS lost to a concurrent writer of the same entry, a bucket
-// whose chunk is full) takes the one-record-at-a-time path (upsert_from / bucket_place_slow).
-template <int KEYW>
+// What does not fit the straight line (directory collision, a CAS lost to a concurrent writer, a bucket whose chunk is
+// full) takes the one-record-at-a-time path (upsert_from / bucket_place_slow).
+template <int KEYW, int VALW>
 __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
                                                         const unsigned long long *__restrict__ n_ptr, unsigned long long n_max)
 {
+    typedef typename ValT<VALW>::T T;
     constexpr int XW = KEYW == 1 ? 3 : 4;
-    constexpr int ES = KEYW == 1 ? 2 : 4;
     constexpr int PF = 4;
-    enum { DONE = 0, KEY = 1, VAL = 2, PUSH = 3, WALK = 4 };
+    enum { DONE = 0, DIR = 1, VAL = 2, PUSH = 3, WALK = 4 };
     SearchCtrl *c = d.ctrl;
     {   // warp-uniform early exit: other CTAs of this launch may raise c->error, and warp-level ballots follow
         int skip = (threadIdx.x & 31) == 0 ? c->error : 0;
@@ -1314,7 +1393,7 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
         k.lo = it[0];
         if constexpr (KEYW == 2) k.hi = it[1];
         const unsigned long long g_f = it[KEYW], m = it[KEYW + 1];
-        const unsigned fl = upsert_from<KEYW>(d, k, m >> 32, (int)(unsigned)(g_f >> 32), (int)(unsigned)g_f, (int)(m & 0xffffu));
+        const unsigned fl = upsert_from<KEYW, VALW>(d, k, m >> 32, (int)(unsigned)(g_f >> 32), (int)(unsigned)g_f, (int)(m & 0xffffu));
         cn.inserted += fl & UPS_INSERTED;
         cn.pushed += (fl >> 1) & 1u;
         cn.reopen += (fl >> 2) & 1u;
@@ -1323,9 +1402,10 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
     const long long stride = (long long)gridDim.x * blockDim.x;
     // the trip count is warp-uniform: the deferred ring is a warp-level structure
     for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * PF) {
-        Key<KEYW> key[PF];
-        unsigned long long gf[PF], lk[PF], lv[PF], lw[KEYW == 2 ? PF : 1];
-        uint32_t st[PF];
+        Key<KEYW> key[PF], bkey[PF];
+        unsigned long long gf[PF], h0[PF], h1[KEYW == 2 ? PF : 1];
+        T lv[PF], lo[PF];
+        uint32_t st[PF]; // directory slot
         unsigned mk[PF];
         int state[PF];
         // ---- records
@@ -1334,10 +1414,12 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
             const long long i = i0 + j * stride;
             state[j] = DONE;
             key[j] = Key<KEYW>::zero();
+            bkey[j] = Key<KEYW>::zero();
             gf[j] = 0;
             mk[j] = 0;
             st[j] = 0;
-            lk[j] = lv[j] = 0;
+            h0[j] = 0;
+            lv[j] = lo[j] = 0;
             if (i < n) {
                 const unsigned long long *r = recs + i * XW;
                 key[j].lo = __ldcs(r);
@@ -1346,10 +1428,10 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
                 const unsigned long long m = __ldcs(r + KEYW + 1);
                 mk[j] = (unsigned)m & 0xffffu;
                 st[j] = (uint32_t)(m >> 32);
-                state[j] = mk[j] == 0 ? DONE : ((m & HINT_FLAG) ? VAL : KEY); // move mask 0: hole left by the sender's chunked outbox
+                state[j] = mk[j] == 0 ? DONE : ((m & HINT_FLAG) ? VAL : DIR); // move mask 0: hole left by the sender's chunked outbox
             }
         }
-        // ---- table entries
+        // ---- goal / pruning; directory words of the records that carry no directory slot
 #pragma unroll
         for (int j = 0; j < PF; j++) {
             if (state[j] == DONE) continue;
@@ -1364,81 +1446,85 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
                 state[j] = DONE;
                 continue;
             }
-            if (state[j] == KEY) st[j] = (uint32_t)home_slot<KEYW>(key[j], d.kb, d.cap_mask); // no slot hint in the record
-            const unsigned long long *e = d.table + (size_t)st[j] * ES;
-            ld_cg_v2(e, lk[j], lv[j]);
-            if constexpr (KEYW == 2) lw[j] = ld_cg_u64(e + 2);
+            bkey[j] = block_key<KEYW>(d, key[j]);
+            if (state[j] == DIR) {
+                st[j] = (uint32_t)dir_home<KEYW>(d, key[j], dir_pos<KEYW>(d, key[j]));
+                const unsigned long long *e = d.dir + (size_t)st[j] * KEYW;
+                if constexpr (KEYW == 1)
+                    h0[j] = ld_cg_u64(e);
+                else
+                    ld_cg_v2(e, h0[j], h1[j]);
+            }
         }
-        // ---- classify; CAS the key of the empty slots
+        // ---- resolve the block: found, or claim the free slot (a new block: its values are all empty)
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            if (state[j] == DONE) continue;
-            unsigned long long *e = d.table + (size_t)st[j] * ES;
-            const unsigned gnew = (unsigned)(gf[j] >> 32);
-            if constexpr (KEYW == 1) {
-                if (lk[j] == key[j].lo + 1) {
-                    state[j] = gnew < (unsigned)((~lv[j]) >> 32) ? VAL : DONE; // not better: drop
-                } else if (lk[j] == 0) {
-                    state[j] = KEY;
-                    lk[j] = atomicCAS(e, 0ull, key[j].lo + 1);
-                } else {
-                    state[j] = WALK;
-                    st[j] = (uint32_t)next_slot<KEYW>(st[j], d.cap_mask);
-                }
+            if (state[j] != DIR) continue;
+            unsigned long long w1 = 0;
+            if constexpr (KEYW == 2) w1 = h1[j];
+            if (dir_is<KEYW>(h0[j], w1, bkey[j])) {
+                state[j] = VAL;
+            } else if (h0[j] == 0 && w1 == 0) {
+                unsigned long long *e = d.dir + (size_t)st[j] * KEYW;
+                unsigned long long p0, p1 = 0;
+                if constexpr (KEYW == 1)
+                    p0 = atomicCAS(e, 0ull, bkey[j].lo + 1);
+                else
+                    cas128(e, bkey[j].lo, bkey[j].hi | (1ull << 63), p0, p1);
+                state[j] = ((p0 == 0 && p1 == 0) || dir_is<KEYW>(p0, p1, bkey[j])) ? VAL : WALK; // lost the slot to another block: walk on
             } else {
-                if (lk[j] == key[j].lo && lv[j] == (key[j].hi | (1ull << 63))) {
-                    state[j] = gnew < (unsigned)((~lw[j]) >> 32) ? VAL : DONE;
-                    lv[j] = lw[j];
-                } else if (lk[j] == 0 && lv[j] == 0) {
-                    state[j] = KEY;
-                    cas128(e, key[j].lo, key[j].hi | (1ull << 63), lk[j], lv[j]);
-                } else {
-                    state[j] = WALK;
-                    st[j] = (uint32_t)next_slot<KEYW>(st[j], d.cap_mask);
-                }
+                state[j] = WALK; // collision: the walk continues from the next line
+                st[j] = (uint32_t)dir_next<KEYW>(d, st[j]);
             }
         }
-        // ---- CAS the value where this record is strictly better (lv = the value the CAS expects)
+        // ---- values
+        uint32_t vs[PF]; // value slot
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            if (state[j] == KEY) {
-                const bool won = KEYW == 1 ? lk[j] == 0 : (lk[j] == 0 && lv[j] == 0);
-                if (won) {
-                    cn.inserted++;
-                    lv[j] = 0;
-                    state[j] = VAL;
-                } else {
-                    state[j] = WALK; // lost the slot to a concurrent insert (of this key or another): re-read it
-                }
+            vs[j] = 0;
+            if (state[j] != VAL) continue;
+            vs[j] = (uint32_t)(((unsigned long long)st[j] << d.D) | block_index<KEYW>(d, key[j]));
+            lv[j] = ld_val<VALW>(val_ptr<VALW>(d, vs[j]));
+        }
+        // ---- CAS the value where this record is strictly better (lv = the value the CAS expects, lo = what it found)
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            if (state[j] != VAL) continue;
+            const unsigned gnew = (unsigned)(gf[j] >> 32);
+            if (gnew >= val_g<VALW>(d, lv[j])) {
+                state[j] = DONE; // not better: drop (PAStar.cpp:228 / PriorityList.h:109)
+                continue;
             }
-            if (state[j] == VAL) {
-                const unsigned long long mine = ~((gf[j] & 0xffffffff00000000ull) | OPEN_BIT | (unsigned long long)mk[j]);
-                lk[j] = atomicCAS(val_ptr<KEYW>(d, st[j]), lv[j], mine);
-            }
+            lo[j] = atomicCAS(val_ptr<VALW>(d, vs[j]), lv[j], val_pack<VALW>(d, gnew, mk[j]));
         }
         // ---- bucket positions for the records that went in
         int bk[PF];
+        unsigned long long bst[PF];
 #pragma unroll
         for (int j = 0; j < PF; j++) {
             bk[j] = -1;
+            bst[j] = 0;
             if (state[j] != VAL) continue;
-            if (lk[j] == lv[j]) {
-                if (lv[j] != 0 && !((~lv[j]) & OPEN_BIT)) cn.reopen++; // was closed with a worse g: PAStar.cpp:230-231
+            if (lo[j] == lv[j]) {
+                if (lv[j] == 0)
+                    cn.inserted++;
+                else if (val_closed<VALW>(d, lv[j]))
+                    cn.reopen++; // was closed with a worse g: PAStar.cpp:230-231
                 cn.pushed++;
                 bk[j] = bucket_of(d, (int)(unsigned)gf[j]);
                 state[j] = bk[j] >= 0 ? PUSH : DONE;
                 if (bk[j] >= 0) {
                     min_b = min(min_b, bk[j]);
-                    lk[j] = atomicAdd(d.buckets + bk[j], 1ull);
+                    bst[j] = atomicAdd(d.buckets + bk[j], 1ull);
                 }
             } else {
                 // a concurrent writer changed the value: still better than what is there now?
-                state[j] = (unsigned)(gf[j] >> 32) < (unsigned)((~lk[j]) >> 32) ? WALK : DONE;
+                state[j] = (unsigned)(gf[j] >> 32) < val_g<VALW>(d, lo[j]) ? WALK : DONE;
             }
         }
 #pragma unroll
         for (int j = 0; j < PF; j++)
-            if (state[j] == PUSH) bucket_place(d, bk[j], st[j], lk[j]);
+            if (state[j] == PUSH) bucket_place(d, bk[j], vs[j], bst[j]);
         // ---- everything else goes to the warp's deferred ring and is handled 32 at a time with every lane busy (about
         //      1 % of the records: done in place, one straggling lane would stall its warp in most iterations)
 #pragma unroll
@@ -1486,18 +1572,15 @@ __global__ void publish_counts_kernel(const __grid_constant__ DevSearch d)
 
 
 // Seed: insert the start node (Sequences::get_initial_node, Sequences.cpp:70-77; PAStar.cpp:153).
-template <int KEYW>
-__global__ void seed_kernel(const __grid_constant__ DevSearch d, int f, int parenti, int as_goal_g)
+template <int KEYW, int VALW>
+__global__ void seed_kernel(const __grid_constant__ DevSearch d, int f, int parenti)
 {
-    Key<KEYW> key = Key<KEYW>::zero();
-    unsigned long long val;
-    bool fresh;
-    const unsigned long long slot = table_slot<KEYW>(d, key, val, fresh);
-    *val_ptr<KEYW>(d, slot) = ~((0ull << 32) | OPEN_BIT | (unsigned long long)(unsigned)parenti);
+    const Key<KEYW> key = Key<KEYW>::zero();
+    const unsigned long long slot = table_find<KEYW>(d, key, true);
+    *val_ptr<VALW>(d, slot) = val_pack<VALW>(d, 0u, (unsigned)parenti);
     bucket_push(d, f, (uint32_t)slot);
     d.ctrl->inserted = 1;
     d.ctrl->pushed = 1;
-    (void)as_goal_g;
 }
 
 // Cost of the all-sequences-advance path: a valid alignment, hence an upper bound on g*.
@@ -1535,7 +1618,7 @@ __global__ void ub_kernel(const __grid_constant__ DevProblem p, int *out)
 }
 
 // Walk parenti from the final coordinate to the origin (backtrace.cpp:44-69); one thread.
-template <int KEYW>
+template <int KEYW, int VALW>
 __global__ void backtrace_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d, uint32_t *out, int max_cols)
 {
     int pos[PG_MAX_SEQ];
@@ -1550,38 +1633,14 @@ __global__ void backtrace_kernel(const __grid_constant__ DevProblem p, const __g
             key.add_val((unsigned)pos[i], i * p.key_bits);
         }
         if (origin || cols >= max_cols) break;
-        // read-only probe
-        constexpr int ES = KEYW == 1 ? 2 : 4;
-        unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
-        unsigned long long val = 0;
-        bool found = false;
-        for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
-            const unsigned long long *e = d.table + slot * ES;
-            if constexpr (KEYW == 1) {
-                if (e[0] == key.lo + 1) {
-                    val = e[1];
-                    found = true;
-                    break;
-                }
-                if (e[0] == 0) break;
-            } else {
-                unsigned long long w1 = 1ull << 63;
-                if constexpr (KEYW == 2) w1 |= key.hi;
-                if (e[0] == key.lo && e[1] == w1) {
-                    val = e[2];
-                    found = true;
-                    break;
-                }
-                if (e[0] == 0 && e[1] == 0) break;
-            }
-        }
-        if (!found) {
+        const unsigned long long slot = table_find<KEYW>(d, key, false); // read-only probe
+        const typename ValT<VALW>::T val = slot == ~0ull ? 0 : *val_ptr<VALW>(d, slot);
+        if (val == 0) {
             out[0] = 0xffffffffu;
             return;
         }
-        const unsigned long long v = ~val;
-        if (cols == 0) g_final = (int)(unsigned)(v >> 32);
-        const unsigned mask = (unsigned)(v & 0xffffu);
+        if (cols == 0) g_final = (int)val_g<VALW>(d, val);
+        const unsigned mask = val_mask<VALW>(d, val);
         out[2 + cols] = mask;
         cols++;
         for (int i = 0; i < p.n; i++) pos[i] -= (mask >> i) & 1;
@@ -1591,58 +1650,38 @@ __global__ void backtrace_kernel(const __grid_constant__ DevProblem p, const __g
 }
 
 // Host-side table lookup of one coordinate (distributed backtrace).
-template <int KEYW>
+template <int KEYW, int VALW>
 __global__ void lookup_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d, const uint16_t *pos, int *out)
 {
     Key<KEYW> key = Key<KEYW>::zero();
     for (int i = 0; i < p.n; i++) key.add_val((unsigned)pos[i], i * p.key_bits);
-    constexpr int ES = KEYW == 1 ? 2 : 4;
-    unsigned long long slot = home_slot<KEYW>(key, d.kb, d.cap_mask);
     out[0] = 0;
-    for (int probe = 0; probe < MAX_PROBE; probe++, slot = next_slot<KEYW>(slot, d.cap_mask)) {
-        const unsigned long long *e = d.table + slot * ES;
-        bool hit, empty;
-        unsigned long long val;
-        if constexpr (KEYW == 1) {
-            hit = e[0] == key.lo + 1;
-            empty = e[0] == 0;
-            val = e[1];
-        } else {
-            unsigned long long w1 = 1ull << 63;
-            if constexpr (KEYW == 2) w1 |= key.hi;
-            hit = e[0] == key.lo && e[1] == w1;
-            empty = e[0] == 0 && e[1] == 0;
-            val = e[2];
-        }
-        if (hit) {
-            const unsigned long long v = ~val;
-            out[0] = 1;
-            out[1] = (int)(unsigned)(v >> 32);
-            out[2] = (int)(v & 0xffffu);
-            out[3] = (v & OPEN_BIT) ? 1 : 0;
-            return;
-        }
-        if (empty) return;
-    }
+    const unsigned long long slot = table_find<KEYW>(d, key, false);
+    if (slot == ~0ull) return;
+    const typename ValT<VALW>::T val = *val_ptr<VALW>(d, slot);
+    if (val == 0) return;
+    out[0] = 1;
+    out[1] = (int)val_g<VALW>(d, val);
+    out[2] = (int)val_mask<VALW>(d, val);
+    out[3] = val_closed<VALW>(d, val) ? 0 : 1;
 }
 
-// Count open / closed entries at the end (PAStar.cpp:591-619 report).
-template <int KEYW>
+// Count open / closed entries at the end (PAStar.cpp:591-619 report): every value of every block in use.
+template <int KEYW, int VALW>
 __global__ void census_kernel(const __grid_constant__ DevSearch d, unsigned long long *out)
 {
-    constexpr int ES = KEYW == 1 ? 2 : 4;
     unsigned long long open = 0, closed = 0;
-    const unsigned long long cap = d.cap_mask + 1;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long *e = d.table + i * ES;
-        const bool live = KEYW == 1 ? e[0] != 0 : (e[0] != 0 || e[1] != 0);
-        if (!live) continue;
-        const unsigned long long v = ~e[KEYW == 1 ? 1 : 2];
-        if (e[KEYW == 1 ? 1 : 2] == 0) continue; // claimed but never valued
-        if (v & OPEN_BIT)
-            open++;
-        else
+    const unsigned long long nvals = (d.dir_mask + 1) << d.D;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nvals; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long *e = d.dir + (i >> d.D) * KEYW;
+        const bool used = KEYW == 1 ? e[0] != 0 : (e[0] != 0 || e[1] != 0);
+        if (!used) continue;
+        const typename ValT<VALW>::T val = *val_ptr<VALW>(d, i);
+        if (val == 0) continue;
+        if (val_closed<VALW>(d, val))
             closed++;
+        else
+            open++;
     }
     for (int o = 16; o; o >>= 1) {
         open += __shfl_down_sync(0xffffffffu, open, o);
@@ -1659,6 +1698,21 @@ __global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v, lon
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// run STMT with KW / VW bound to the table's key width (u64 words) and value width (bytes): (1,4), (1,8) or (2,8)
+#define PG_DISPATCH_KV(s, STMT)                  \
+    do {                                         \
+        if ((s)->keyw == 1 && (s)->valw == 4) {  \
+            constexpr int KW = 1, VW = 4;        \
+            STMT;                                \
+        } else if ((s)->keyw == 1) {             \
+            constexpr int KW = 1, VW = 8;        \
+            STMT;                                \
+        } else {                                 \
+            constexpr int KW = 2, VW = 8;        \
+            STMT;                                \
+        }                                        \
+    } while (0)
+
 int ilog2i(int v)
 {
     int l = 0;
@@ -1670,9 +1724,24 @@ DevSearch dev_search(const pg_ctx *ctx)
 {
     const SearchState *s = ctx->search;
     DevSearch d;
-    d.table = (unsigned long long *)s->d_table;
-    d.cap_mask = s->cap - 1;
+    d.dir = s->d_dir;
+    d.dir_mask = s->dir_slots - 1;
+    d.vals = s->d_vals;
     d.kb = ctx->dp.key_bits;
+    d.D = s->D;
+    d.DL = s->DL;
+    d.nb = s->nb;
+    d.gs = s->gs;
+    {
+        unsigned __int128 low = 0, line = 0;
+        for (int i = 0; i < s->D; i++) low |= (unsigned __int128)1 << (i * ctx->dp.key_bits);
+        line = low;
+        for (int i = 0; i < s->DL; i++) line |= (unsigned __int128)1 << (i * ctx->dp.key_bits + 1);
+        d.low_lo = (unsigned long long)low;
+        d.low_hi = (unsigned long long)(low >> 64);
+        d.line_lo = (unsigned long long)line;
+        d.line_hi = (unsigned long long)(line >> 64);
+    }
     d.buckets = s->d_buckets;
     d.tail = s->d_tail;
     d.hint = s->d_hint;
@@ -1736,7 +1805,7 @@ OwnerArgs owner_args(const pg_ctx *ctx)
 
 // MODE as in expand_probe_kernel; inbox = false: this partition's own live parents, true: the parents forwarded by the
 // other partitions (MODE 2)
-template <int N, int KEYW, int MODE>
+template <int N, int KEYW, int VALW, int MODE>
 int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
 {
     using C = ExpCfg<N>;
@@ -1748,8 +1817,8 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
     // per-device state (cudaFuncSetAttribute applies to the current device only): cached per context and kernel mode
     int &occ = ctx->occ_expand_probe[MODE];
     if (!occ) {
-        PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, MODE>, 256, smem));
+        PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, VALW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, VALW, MODE>, 256, smem));
         if (occ < 1) occ = 1;
     }
     // persistent grid: resident CTAs per SM x SM count, capped by the parent groups of a full batch
@@ -1775,12 +1844,12 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
             ps.n++;
         }
     }
-    expand_probe_kernel<N, KEYW, MODE><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, d, owner_args(ctx), ps);
+    expand_probe_kernel<N, KEYW, VALW, MODE><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, d, owner_args(ctx), ps);
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
 }
 
-template <int KEYW>
+template <int KEYW, int VALW>
 int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st, bool inbox = false)
 {
     const SearchState *s = ctx->search;
@@ -1788,9 +1857,9 @@ int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st, bool inbox = false)
     switch (ctx->n) {
 #define CASE(X)                                                                    \
     case X:                                                                        \
-        if (mode == 0) return launch_expand_round<X, KEYW, 0>(ctx, st, inbox);     \
-        if (mode == 1) return launch_expand_round<X, KEYW, 1>(ctx, st, inbox);     \
-        return launch_expand_round<X, KEYW, 2>(ctx, st, inbox);
+        if (mode == 0) return launch_expand_round<X, KEYW, VALW, 0>(ctx, st, inbox);     \
+        if (mode == 1) return launch_expand_round<X, KEYW, VALW, 1>(ctx, st, inbox);     \
+        return launch_expand_round<X, KEYW, VALW, 2>(ctx, st, inbox);
         CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(14) CASE(16)
 #undef CASE
     }
@@ -1850,10 +1919,7 @@ int launch_insert(pg_ctx *ctx, const void *recs, const unsigned long long *n_ptr
     SearchState *s = ctx->search;
     if (n_max == 0) return PG_OK;
     const long long grid = std::min<long long>((long long)((n_max + 1023) / 1024), (long long)ctx->sm_count * 8);
-    if (s->keyw == 1)
-        insert_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max);
-    else
-        insert_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max);
+    PG_DISPATCH_KV(s, (insert_kernel<KW, VW><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max)));
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
 }
@@ -1880,10 +1946,7 @@ int launch_round(pg_ctx *ctx, int f_limit)
         const long long grid = std::min<long long>((s->batch_target + 1023) / 1024, (long long)ctx->sm_count * 8); // claim: 4 pops per thread
         const long long fgrid = std::min<long long>((s->batch_target + 255) / 256, (long long)ctx->sm_count * 8);
         const DevSearch d = dev_search(ctx);
-        if (s->keyw == 1)
-            claim_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(d);
-        else
-            claim_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(d);
+        PG_DISPATCH_KV(s, (claim_kernel<KW, VW><<<(unsigned)grid, 256, 0, ctx->stream>>>(d)));
         PG_CUDA(ctx, cudaGetLastError());
         if (s->forward) { // the parents and their counts leave at once: they travel while this partition expands its own
             const OwnerArgs oa = owner_args(ctx);
@@ -1898,7 +1961,7 @@ int launch_round(pg_ctx *ctx, int f_limit)
     }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     if (!s->merge_expand) {
-        rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream) : launch_expand_round_k<2>(ctx, ctx->stream);
+        PG_DISPATCH_KV(s, (rc = launch_expand_round_k<KW, VW>(ctx, ctx->stream)));
         if (rc != PG_OK) return rc;
     }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
@@ -1968,7 +2031,8 @@ void pg_search_free(pg_ctx *ctx)
 {
     SearchState *s = ctx->search;
     if (!s) return;
-    cudaFree(s->d_table);
+    cudaFree(s->d_dir);
+    cudaFree(s->d_vals);
     cudaFree(s->d_buckets);
     cudaFree(s->d_tail);
     cudaFree(s->d_hint);
@@ -2010,29 +2074,9 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     s->keyw = ctx->n * ctx->dp.key_bits <= 63 ? 1 : 2;
     if (s->keyw == 2 && ctx->n * ctx->dp.key_bits > 127) return pg_fail(ctx, PG_ERR_UNSUPPORTED, "packed coordinate key exceeds 127 bits");
     s->xrec = pg_xrec_stride(ctx);
-    const size_t entry = s->keyw == 1 ? 16 : 32;
-
-    // ---- capacity: explicit, or a fraction of the free memory
-    size_t free_b = 0, total_b = 0;
-    PG_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    uint64_t cap = cfg->table_capacity > 0 ? (uint64_t)cfg->table_capacity : 0;
-    if (cap == 0) {
-        cap = 1;
-        while (cap * 2 * (entry + 24) <= free_b / 2 && cap * 2 <= (1ull << 32)) cap *= 2; // table + open-list pool: about half of what is free
-        // ... but never more than twice the lattice itself: there are only prod(len + 1) coordinates (small inputs would
-        // otherwise spend their whole run time allocating and clearing tens of GB)
-        long double lattice = 1.0L;
-        for (int i = 0; i < ctx->n; i++) lattice *= (long double)(ctx->len[i] + 1);
-        uint64_t need = 1024;
-        while ((long double)need < 2.0L * lattice && need < cap) need *= 2;
-        cap = std::min(cap, need);
-    } else {
-        uint64_t c2 = 1024;
-        while (c2 < cap) c2 *= 2;
-        cap = c2;
-    }
-    if (cap > (1ull << 32)) cap = 1ull << 32; // u32 slot ids in the open buckets
-    s->cap = cap;
+    s->D = std::min(ctx->n, 7);
+    s->DL = ctx->dp.key_bits >= 2 ? std::min(ctx->n, s->keyw == 1 ? 4 : 3) : 0;
+    ctx->occ_expand_probe[0] = ctx->occ_expand_probe[1] = ctx->occ_expand_probe[2] = 0; // the value width may differ from the last search's
 
     s->batch_target = cfg->batch_target > 0 ? cfg->batch_target : 16384;
 
@@ -2060,9 +2104,44 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
         return pg_fail(ctx, PG_ERR_UNSUPPORTED, "f range (upper bound - h(start)) exceeds 2^27 open-list buckets");
     s->f_range = (int)range;
 
+    // ---- value width: 4 bytes when g (<= the upper bound), the open bit and the move mask fit 32 bits
+    {
+        const char *fv = getenv("PG_VALW"); // PG_VALW=8 forces the wide form (tests)
+        const bool fits = s->keyw == 1 && (unsigned long long)s->ub + 2ull < (1ull << (31 - ctx->n));
+        s->valw = (fits && !(fv && atoi(fv) == 8)) ? 4 : 8;
+        s->nb = s->valw == 4 ? ctx->n : 31;
+        s->gs = s->nb + 1;
+    }
+    // ---- capacity.  table_capacity counts the coordinates the caller wants room for; blocks are cubes of 2^D
+    //      coordinates of which a search fills a part (the frontier's surface cuts through them), so four value slots are
+    //      provided per coordinate: 16 B per coordinate with 4-byte values, as much as a keyed 16-byte entry took.
+    {
+        size_t free_b = 0, total_b = 0;
+        PG_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t per_coord = 4ull * (uint64_t)s->valw + 24; // values + open-list pool share
+        uint64_t want = cfg->table_capacity > 0 ? (uint64_t)cfg->table_capacity : 0;
+        if (want == 0) {
+            want = 1024;
+            while (want * 2 * per_coord <= free_b / 2 && want * 2 <= (1ull << 30)) want *= 2; // about half of what is free
+            // ... but never more than the lattice itself (small inputs would otherwise spend their run time clearing GBs)
+            long double lattice = 1.0L;
+            for (int i = 0; i < ctx->n; i++) lattice *= (long double)(ctx->len[i] + 2);
+            uint64_t need = 1024;
+            while ((long double)need < lattice && need < want) need *= 2;
+            want = std::min(want, need);
+        }
+        uint64_t slots = 1ull << (s->D + 5); // at least two directory lines
+        while (slots < 4 * want && slots < (1ull << 32)) slots *= 2; // u32 slot ids in the open buckets
+        s->cap = slots;
+        s->dir_slots = slots >> s->D;
+    }
+    const uint64_t cap = std::max<uint64_t>(s->cap / 4, 1024); // coordinates provided for: sizes the open-list pool
+
     // ---- allocations
-    PG_CUDA(ctx, cudaMalloc(&s->d_table, cap * entry));
-    PG_CUDA(ctx, cudaMemsetAsync(s->d_table, 0, cap * entry, ctx->stream));
+    PG_CUDA(ctx, cudaMalloc(&s->d_dir, (size_t)s->dir_slots * 8 * s->keyw));
+    PG_CUDA(ctx, cudaMemsetAsync(s->d_dir, 0, (size_t)s->dir_slots * 8 * s->keyw, ctx->stream));
+    PG_CUDA(ctx, cudaMalloc(&s->d_vals, (size_t)s->cap * s->valw));
+    PG_CUDA(ctx, cudaMemsetAsync(s->d_vals, 0, (size_t)s->cap * s->valw, ctx->stream));
     PG_CUDA(ctx, cudaMalloc(&s->d_buckets, (size_t)s->f_range * 8));
     PG_CUDA(ctx, cudaMalloc(&s->d_tail, (size_t)s->f_range * 4));
     PG_CUDA(ctx, cudaMemsetAsync(s->d_tail, 0, (size_t)s->f_range * 4, ctx->stream));
@@ -2135,10 +2214,7 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     // (get_id of the origin is 0 for every hash) which is partition 0 as well.
     if (cfg->part == 0) {
         const int parenti = (1 << ctx->n) - 1; // Sequences.cpp:75
-        if (s->keyw == 1)
-            seed_kernel<1><<<1, 1, 0, ctx->stream>>>(dev_search(ctx), s->f0, parenti, 0);
-        else
-            seed_kernel<2><<<1, 1, 0, ctx->stream>>>(dev_search(ctx), s->f0, parenti, 0);
+        PG_DISPATCH_KV(s, (seed_kernel<KW, VW><<<1, 1, 0, ctx->stream>>>(dev_search(ctx), s->f0, parenti)));
         PG_CUDA(ctx, cudaGetLastError());
     }
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2226,7 +2302,7 @@ extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
     if (s->forward) {
         // expand the parents the other partitions forwarded (only the successors this partition owns), then insert
         // the round's survivors: those of its own parents and of the forwarded ones
-        rc = s->keyw == 1 ? launch_expand_round_k<1>(ctx, ctx->stream, true) : launch_expand_round_k<2>(ctx, ctx->stream, true);
+        PG_DISPATCH_KV(s, (rc = launch_expand_round_k<KW, VW>(ctx, ctx->stream, true)));
         if (rc != PG_OK) return rc;
         if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
     } else {
@@ -2322,10 +2398,7 @@ extern "C" int pg_search_lookup(pg_ctx *ctx, const uint16_t *pos, int32_t *found
     uint16_t *d_pos = (uint16_t *)s->d_trace;
     int *d_out = (int *)(s->d_trace + 64);
     PG_CUDA(ctx, cudaMemcpyAsync(d_pos, pos, ctx->n * 2, cudaMemcpyHostToDevice, ctx->stream));
-    if (s->keyw == 1)
-        lookup_kernel<1><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), d_pos, d_out);
-    else
-        lookup_kernel<2><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), d_pos, d_out);
+    PG_DISPATCH_KV(s, (lookup_kernel<KW, VW><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), d_pos, d_out)));
     PG_CUDA(ctx, cudaGetLastError());
     int h[4];
     PG_CUDA(ctx, cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2420,10 +2493,7 @@ extern "C" int pg_search(pg_ctx *ctx, const pg_search_config *cfg_in, pg_result 
     {
         unsigned long long *d_cnt = (unsigned long long *)s->d_trace;
         PG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
-        if (s->keyw == 1)
-            census_kernel<1><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
-        else
-            census_kernel<2><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
+        PG_DISPATCH_KV(s, (census_kernel<KW, VW><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt)));
         unsigned long long h[2];
         PG_CUDA(ctx, cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
         PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2435,10 +2505,7 @@ extern "C" int pg_search(pg_ctx *ctx, const pg_search_config *cfg_in, pg_result 
         res->g = res->f = s->h_ctrl->best_goal; // h(goal) = 0
         int total = 0;
         for (int i = 0; i < ctx->n; i++) total += ctx->len[i];
-        if (s->keyw == 1)
-            backtrace_kernel<1><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), s->d_trace, total);
-        else
-            backtrace_kernel<2><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), s->d_trace, total);
+        PG_DISPATCH_KV(s, (backtrace_kernel<KW, VW><<<1, 1, 0, ctx->stream>>>(ctx->dp, dev_search(ctx), s->d_trace, total)));
         PG_CUDA(ctx, cudaGetLastError());
         std::vector<uint32_t> tr((size_t)total + 2);
         PG_CUDA(ctx, cudaMemcpyAsync(tr.data(), s->d_trace, tr.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2481,10 +2548,7 @@ int census_ctx(pg_ctx *ctx, int64_t *open_size, int64_t *closed_size)
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned long long *d_cnt = (unsigned long long *)s->d_trace;
     PG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
-    if (s->keyw == 1)
-        census_kernel<1><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
-    else
-        census_kernel<2><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt);
+    PG_DISPATCH_KV(s, (census_kernel<KW, VW><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dev_search(ctx), d_cnt)));
     unsigned long long h[2];
     PG_CUDA(ctx, cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
