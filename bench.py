@@ -371,6 +371,11 @@ def run_ours(args, rank, world):
                 line["roofline"]["traffic"] = json.load(open(tr)).get(top)
             except Exception:
                 pass
+        if args.quick:  # kernel-tuning runs: the round's timing only
+            line["extra"] = {"quick": True}
+            print(json.dumps(line), flush=True)
+            G.close()
+            return
         # ---- pairwise DP and stand-alone expansion kernel (the other two headline kernels)
         st = stream.cuda_stream
         Kx = 100000
@@ -537,6 +542,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="open-list entries popped per round and GPU")
     ap.add_argument("--table-capacity", type=int, default=1 << 30)
+    ap.add_argument("--quick", action="store_true", help="N = 1: print the round's timing only (no extras, e2e or CPU baseline)")
     ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the untimed PF08184 / kinase parity gate (profiling runs)")
     ap.add_argument("--hash-shift", type=int, default=17,
                     help="FZORDER owner-hash shift for N > 1 (the reference's -s, 0..21; its default 12 puts owner bits at bit 1 of two coordinates, 17 at bit 2 of three: fewer parents straddle partitions)")

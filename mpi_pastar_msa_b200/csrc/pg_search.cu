@@ -315,6 +315,19 @@ __device__ __forceinline__ typename ValT<VALW>::T ld_val(const typename ValT<VAL
         return ld_cg_u64(p);
 }
 
+// asynchronous 4 / 8-byte copy global -> shared: the value load of a probe holds no register while it is in flight
+template <int BYTES>
+__device__ __forceinline__ void cp_async_val(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    if constexpr (BYTES == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- keys -> block key, place inside the block, directory slot
 template <int KEYW>
 __device__ __forceinline__ Key<KEYW> block_key(const DevSearch &d, const Key<KEYW> &key)
@@ -778,6 +791,7 @@ __device__ __forceinline__ unsigned successor_owners(const DevProblem &p, const 
     return set & ~(1u << part);
 }
 
+constexpr uint32_t PROBE_MISS = 0xffffffffu;        // stash: the probe found no block of its own at the home directory slot
 constexpr unsigned long long HINT_FLAG = 1ull << 31; // record word KEYW+1: {start slot : 32 | HINT_FLAG | move mask : 16}
 constexpr int RING_CAP = 64;                         // survivor ring, items per warp
 constexpr int PLAN_SM = 2048;
@@ -1011,13 +1025,18 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     constexpr int GROUPS = 256 / C::LP;
     constexpr int GPW = 32 / C::LP; // parent groups per warp
     constexpr int NI = 1 << C::IB;
-    constexpr int PFMAX = KEYW == 1 ? 8 : 4;
+    constexpr int PFMAX = (KEYW == 1 && N < 14) ? 8 : 4; // N >= 14: the HH tables leave less shared memory for the stash
     constexpr int PF = NI < PFMAX ? NI : PFMAX; // successors whose table loads are in flight together, per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairMeta *meta = reinterpret_cast<PairMeta *>(smem_raw);
     Key<KEYW> *s_keyhigh = reinterpret_cast<Key<KEYW> *>(smem_raw + ((sizeof(PairMeta) + 15) & ~size_t(15)));
     unsigned long long *s_ring = reinterpret_cast<unsigned long long *>(s_keyhigh + C::H); // [8 warps][RING_CAP][XW]
     int *s_groups = reinterpret_cast<int *>(s_ring + 8 * RING_CAP * XW);
+    // probe stash: what the deferred compare of a batch needs, [PF][256] each, a thread only touches its own column
+    T *s_pv = reinterpret_cast<T *>(s_groups + GROUPS * C::GROUP_INTS);      // values (cp.async destination)
+    int *s_pg = reinterpret_cast<int *>(s_pv + PF * 256);                    // g
+    int *s_pf = s_pg + PF * 256;                                             // f
+    uint32_t *s_ps = reinterpret_cast<uint32_t *>(s_pf + PF * 256);          // directory slot, PROBE_MISS when the block was not at its home slot
     __shared__ unsigned long long s_cnt[4];
     __shared__ unsigned long long s_obox[SEND ? 64 : 1];
     __shared__ unsigned char s_mod[MULTI ? 256 : 1]; // owner word -> partition
@@ -1065,6 +1084,49 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     unsigned n_exp = 0, n_gen = 0, n_pruned = 0;
     const unsigned fmask = (1u << p.key_bits) - 1u;
     const int full = (1 << N) - 1;
+
+    // ---- the deferred half of a probe batch: compare the values that have arrived; stage the survivors
+    bool pend = false;          // warp-uniform
+    unsigned pend_vmask = 0;    // which of the batch's PF probes this lane issued
+    int pend_hb = 0;            // high-mask index of the batch's first probe
+    Key<KEYW> pend_klow = Key<KEYW>::zero();
+    auto complete = [&]() {
+        cp_async_wait_all();
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            bool slow = false;
+            uint32_t hit = PROBE_MISS;
+            int gn = 0;
+            if ((pend_vmask >> j) & 1u) {
+                hit = s_ps[j * 256 + threadIdx.x];
+                gn = s_pg[j * 256 + threadIdx.x];
+                // same coordinate, g not better (PAStar.cpp:228 / PriorityList.h:109) ends here: the common case
+                slow = hit == PROBE_MISS || (unsigned)gn < val_g<VALW>(d, s_pv[j * 256 + threadIdx.x]);
+            }
+            const unsigned sb = __ballot_sync(0xffffffffu, slow);
+            if (sb) {
+                if (slow) {
+                    const int high = pend_hb + j;
+                    const Key<KEYW> key = pend_klow.plus(s_keyhigh[high]);
+                    unsigned long long *q = wq + (size_t)((qtail + __popc(sb & lt)) & (RING_CAP - 1)) * XW;
+                    q[0] = key.lo;
+                    if constexpr (KEYW == 2) q[1] = key.hi;
+                    q[KEYW] = ((unsigned long long)(unsigned)gn << 32) | (unsigned)s_pf[j * 256 + threadIdx.x];
+                    // the directory slot is a hint for the insert kernel when this successor's block was found there
+                    q[KEYW + 1] = (hit != PROBE_MISS ? ((unsigned long long)hit << 32) | HINT_FLAG : 0ull) | (unsigned long long)(unsigned)((high << C::A) | sub);
+                }
+                qtail += __popc(sb);
+                __syncwarp();
+                if (qtail - qhead >= 32u) {
+                    ring_flush<XW>(d, wq, qhead, 32u, lane);
+                    qhead += 32u;
+                    __syncwarp();
+                }
+            }
+        }
+        pend = false;
+        PH_MARK(4); // pass 2: wait for the probes, compare, stage
+    };
 
     // parents are dealt to the groups round-robin; the trip count is warp-uniform (the ring is a warp-level structure)
     const int stride = gridDim.x * GROUPS;
@@ -1158,10 +1220,11 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
             pg_expand_block<N>(L, u, vg, vh);
 #pragma unroll
             for (int cb = 0; cb < NI; cb += PF) {
+                // the previous batch (of this parent, or the last one of the previous parent: its value loads travelled
+                // while this parent's LUTs were staged) is compared before its stash is reused
+                if (pend) complete();
                 unsigned long long h0[PF], h1[KEYW == 2 ? PF : 1]; // directory words
-                T lv[PF];                                            // values
                 uint32_t ls[PF];                                     // directory slots
-                int lg[PF];
                 unsigned vmask = 0;
                 // ---- pass 1a: f, pruning, owner; ISSUE the directory loads (L1 / L2: neighbouring successors share words)
 #pragma unroll
@@ -1171,12 +1234,10 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     const int mask = (high << C::A) | sub;
                     bool v = act && mask != 0 && (interior || !(mask & ~L.alive));
                     bool rem = false;
-                    int rown = 0;
+                    int rown = 0, gn = 0, fn = 0;
                     h0[j] = 0;
                     if constexpr (KEYW == 2) h1[j] = 0;
-                    lv[j] = 0;
                     ls[j] = 0;
-                    lg[j] = 0;
                     int own = d.part;
                     if constexpr (MULTI) {
                         if (v) {
@@ -1199,14 +1260,14 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                         }
                     }
                     if (v) {
-                        const int gn = vg[i] + s_hhg[high];
-                        const int f = gn + vh[i] + s_hhh[high];
+                        gn = vg[i] + s_hhg[high];
+                        fn = gn + vh[i] + s_hhh[high];
                         n_gen++;
                         const bool is_goal = mask == goal_mask;
                         // a goal (f == g) beyond the upper bound can never be optimal - UB is the cost of a valid
                         // alignment - and one worse than the best goal known is useless: both are dropped like any
                         // other successor, so nothing past the bucket range is ever pushed
-                        bool drop = f >= limit;
+                        bool drop = fn >= limit;
                         if (is_goal) {
                             drop = gn >= prune || gn > best0;
                             if (!drop) atomicMin(&c->best_goal, gn);
@@ -1215,7 +1276,6 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                             n_pruned++;
                             v = false;
                         }
-                        lg[j] = gn;
                     }
                     if (v) {
                         if constexpr (SEND) {
@@ -1238,6 +1298,8 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                                 h0[j] = hh.x;
                                 h1[j] = hh.y;
                             }
+                            s_pg[j * 256 + threadIdx.x] = gn;
+                            s_pf[j * 256 + threadIdx.x] = fn;
                             vmask |= 1u << j;
                         }
                     }
@@ -1253,20 +1315,19 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                             if (rem && rown == dst) {
                                 unsigned long long *r = outbox_record<KEYW>(d, dst, pos0 + __popc(same & lt));
                                 const Key<KEYW> key = klow.plus(s_keyhigh[high]);
-                                const int f = lg[j] + vh[i] + s_hhh[high];
                                 r[0] = key.lo;
                                 if constexpr (KEYW == 2) r[1] = key.hi;
-                                r[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)f;
+                                r[KEYW] = ((unsigned long long)(unsigned)gn << 32) | (unsigned)fn;
                                 r[KEYW + 1] = (unsigned long long)(unsigned)mask;
                             }
                             todo &= ~same;
                         }
                     }
                 }
-                // ---- pass 1b: where the directory word is this successor's block, ISSUE the 4 / 8-byte value load.  No
-                //      block there (free slot: nothing of this cube exists yet) or another block's key (collision): the
-                //      successor goes to the insert kernel, which walks the directory.
-                unsigned hmask = 0;
+                // ---- pass 1b: where the directory word is this successor's block, ISSUE the 4 / 8-byte value load as an
+                //      asynchronous copy into the stash (it holds no register while it travels).  No block there (free slot:
+                //      nothing of this cube exists yet) or another block's key (collision): the successor goes to the
+                //      insert kernel, which walks the directory.
 #pragma unroll
                 for (int j = 0; j < PF; j++) {
                     if ((vmask >> j) & 1u) {
@@ -1276,52 +1337,27 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                         const Key<KEYW> bkey = block_key<KEYW>(d, klow.plus(s_keyhigh[high]));
                         unsigned long long w1 = 0;
                         if constexpr (KEYW == 2) w1 = h1[j];
+                        uint32_t hit = PROBE_MISS;
                         if (dir_is<KEYW>(h0[j], w1, bkey)) {
                             const unsigned idx = (plow ^ (unsigned)mask) & bem;
-                            lv[j] = ld_val<VALW>(val_ptr<VALW>(d, ((unsigned long long)ls[j] << d.D) | idx));
-                            hmask |= 1u << j;
+                            cp_async_val<VALW>(s_pv + j * 256 + threadIdx.x, val_ptr<VALW>(d, ((unsigned long long)ls[j] << d.D) | idx));
+                            hit = ls[j];
                         }
+                        s_ps[j * 256 + threadIdx.x] = hit;
                     }
                 }
+                cp_async_commit();
+                pend = true;
+                pend_vmask = vmask;
+                pend_hb = (u << C::IB) | cb;
+                pend_klow = klow;
                 PH_MARK(3); // pass 1: issue probes (+ remote appends)
-                // ---- pass 2: compare; stage the survivors
-#pragma unroll
-                for (int j = 0; j < PF; j++) {
-                    const int i = cb + j;
-                    const int high = (u << C::IB) | i;
-                    const int mask = (high << C::A) | sub;
-                    bool slow = false;
-                    Key<KEYW> key = Key<KEYW>::zero();
-                    if ((vmask >> j) & 1u) {
-                        key = klow.plus(s_keyhigh[high]);
-                        // same coordinate, g not better (PAStar.cpp:228 / PriorityList.h:109) ends here: the common case
-                        slow = !((hmask >> j) & 1u) || (unsigned)lg[j] < val_g<VALW>(d, lv[j]);
-                    }
-                    const unsigned sb = __ballot_sync(0xffffffffu, slow);
-                    if (sb) {
-                        if (slow) {
-                            unsigned long long *q = wq + (size_t)((qtail + __popc(sb & lt)) & (RING_CAP - 1)) * XW;
-                            q[0] = key.lo;
-                            if constexpr (KEYW == 2) q[1] = key.hi;
-                            q[KEYW] = ((unsigned long long)(unsigned)lg[j] << 32) | (unsigned)(lg[j] + vh[i] + s_hhh[high]);
-                            // the directory slot is a hint for the insert kernel when this successor's block was found there
-                            q[KEYW + 1] = ((unsigned long long)ls[j] << 32) | (((hmask >> j) & 1u) ? HINT_FLAG : 0ull) | (unsigned long long)(unsigned)mask;
-                        }
-                        qtail += __popc(sb);
-                        __syncwarp();
-                        if (qtail - qhead >= 32u) {
-                            ring_flush<XW>(d, wq, qhead, 32u, lane);
-                            qhead += 32u;
-                            __syncwarp();
-                        }
-                    }
-                }
-                PH_MARK(4); // pass 2: wait for the probes, compare, stage
             }
         }
         __syncwarp(); // the group's LUTs are rewritten by the next parent
     }
     } // parent regions
+    if (pend) complete();
     if (qtail != qhead) ring_flush<XW>(d, wq, qhead, qtail - qhead, lane);
     PH_MARK(5);
 #ifdef PG_PHASE_TIMING
@@ -1812,8 +1848,11 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
     SearchState *s = ctx->search;
     constexpr int GROUPS = 256 / C::LP;
     constexpr int XW = KEYW == 1 ? 3 : 4;
+    constexpr int NI = 1 << C::IB;
+    constexpr int PFMAX = (KEYW == 1 && N < 14) ? 8 : 4;
+    constexpr int PF = NI < PFMAX ? NI : PFMAX; // as in the kernel
     const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + 8 * 8 * RING_CAP * XW +
-                        sizeof(int) * (size_t)GROUPS * C::GROUP_INTS;
+                        sizeof(int) * (size_t)GROUPS * C::GROUP_INTS + (size_t)PF * 256 * (VALW + 12);
     // per-device state (cudaFuncSetAttribute applies to the current device only): cached per context and kernel mode
     int &occ = ctx->occ_expand_probe[MODE];
     if (!occ) {
@@ -1860,7 +1899,11 @@ int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st, bool inbox = false)
         if (mode == 0) return launch_expand_round<X, KEYW, VALW, 0>(ctx, st, inbox);     \
         if (mode == 1) return launch_expand_round<X, KEYW, VALW, 1>(ctx, st, inbox);     \
         return launch_expand_round<X, KEYW, VALW, 2>(ctx, st, inbox);
+#ifdef PG_DEV_BUILD // experiment builds (PG_VARIANT=...): only the sizes the measurements use, a third of the compile time
+        CASE(5) CASE(7)
+#else
         CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(14) CASE(16)
+#endif
 #undef CASE
     }
     return pg_fail(ctx, PG_ERR_ARG, "unsupported number of sequences");

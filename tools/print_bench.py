@@ -1,7 +1,7 @@
 """python tools/print_bench.py bench.json : the few numbers of a bench.py line one looks at first."""
 import json, sys
 d = json.load(open(sys.argv[1]))
-print("%d GPU(s): %.1f M expansions/s, %.3f ms/round, e2e %.1f M/s" % (d["n_gpus"], d["value"] / 1e6, d["ms_per_step"], (d["e2e"]["value"] or 0) / 1e6))
+print("%d GPU(s): %.1f M expansions/s, %.3f ms/round, e2e %.1f M/s" % (d["n_gpus"], d["value"] / 1e6, d["ms_per_step"], ((d.get("e2e") or {}).get("value") or 0) / 1e6))
 r = d.get("roofline")
 if r:
     print("roofline: %s frac %.3f of %s GB/s, whole round %.3f, traffic %s" % (r["kernel"], r["frac"], r["peak"], r.get("whole_round_frac", 0), r.get("traffic")))
