@@ -137,15 +137,13 @@ struct Key<1> {
     __device__ __forceinline__ void add_val(unsigned v, int off) { lo += (unsigned long long)v << off; }
     __device__ __forceinline__ Key plus(const Key &o) const { return Key{lo + o.lo}; }
     __device__ __forceinline__ unsigned field(int off, unsigned m) const { return (unsigned)(lo >> off) & m; }
-    // 32-bit mix of the two key halves (the table has at most 2^32 slots): 3 multiplies instead of two 64-bit ones
+    // 32-bit multiplicative mix of the two key halves (the directory has at most 2^28 lines); the caller takes the TOP
+    // bits, which every key bit reaches: two multiplies, one xor-shift, one more multiply
     __device__ __forceinline__ unsigned long long hash() const
     {
         unsigned h = (unsigned)lo * 0x9E3779B1u + (unsigned)(lo >> 32) * 0x85EBCA77u;
         h ^= h >> 15;
         h *= 0xC2B2AE3Du;
-        h ^= h >> 13;
-        h *= 0x27D4EB2Fu;
-        h ^= h >> 16;
         return h;
     }
 };
@@ -177,9 +175,6 @@ struct Key<2> {
                      (unsigned)(hi >> 32) * 0xD3A2646Cu;
         h ^= h >> 15;
         h *= 0xC2B2AE3Du;
-        h ^= h >> 13;
-        h *= 0x27D4EB2Fu;
-        h ^= h >> 16;
         return h;
     }
 };
@@ -230,6 +225,7 @@ struct DevSearch {
     int D;                        // block dimensions: lowest bit of the first D coordinates
     int DL;                       // directory-line dimensions: lowest bit of the first DL BLOCK coordinates
     int nb, gs;                   // value layout: open bit position, g shift (VALW=4: N, N+1; VALW=8: 31, 32)
+    int hshift;                   // 32 - log2(directory lines): the line is the top bits of the 32-bit key hash
     unsigned long long low_lo, low_hi;   // key bits that index inside a block
     unsigned long long line_lo, line_hi; // low bits + the bits that index inside a directory line
     unsigned long long *buckets;
@@ -370,7 +366,7 @@ __device__ __forceinline__ unsigned long long dir_home(const DevSearch &d, const
     Key<KEYW> lk = key;
     lk.lo &= ~d.line_lo;
     if constexpr (KEYW == 2) lk.hi &= ~d.line_hi;
-    return ((lk.hash() << DIR_LB<KEYW>) | dpos) & d.dir_mask;
+    return (((lk.hash() >> d.hshift) << DIR_LB<KEYW>) | dpos) & d.dir_mask; // top bits of the multiplicative hash pick the line
 }
 template <int KEYW>
 __device__ __forceinline__ unsigned long long dir_next(const DevSearch &d, unsigned long long dslot)
@@ -1094,18 +1090,14 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
         cp_async_wait_all();
 #pragma unroll
         for (int j = 0; j < PF; j++) {
-            bool slow = false;
-            uint32_t hit = PROBE_MISS;
-            int gn = 0;
-            if ((pend_vmask >> j) & 1u) {
-                hit = s_ps[j * 256 + threadIdx.x];
-                gn = s_pg[j * 256 + threadIdx.x];
-                // same coordinate, g not better (PAStar.cpp:228 / PriorityList.h:109) ends here: the common case
-                slow = hit == PROBE_MISS || (unsigned)gn < val_g<VALW>(d, s_pv[j * 256 + threadIdx.x]);
-            }
+            // same coordinate, g not better (PAStar.cpp:228 / PriorityList.h:109) ends here: the common case.  A probe that
+            // found no block of its own left an empty value (g = infinity) in the stash.
+            const int gn = s_pg[j * 256 + threadIdx.x];
+            const bool slow = ((pend_vmask >> j) & 1u) && (unsigned)gn < val_g<VALW>(d, s_pv[j * 256 + threadIdx.x]);
             const unsigned sb = __ballot_sync(0xffffffffu, slow);
             if (sb) {
                 if (slow) {
+                    const uint32_t hit = s_ps[j * 256 + threadIdx.x];
                     const int high = pend_hb + j;
                     const Key<KEYW> key = pend_klow.plus(s_keyhigh[high]);
                     unsigned long long *q = wq + (size_t)((qtail + __popc(sb & lt)) & (RING_CAP - 1)) * XW;
@@ -1342,6 +1334,8 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                             const unsigned idx = (plow ^ (unsigned)mask) & bem;
                             cp_async_val<VALW>(s_pv + j * 256 + threadIdx.x, val_ptr<VALW>(d, ((unsigned long long)ls[j] << d.D) | idx));
                             hit = ls[j];
+                        } else {
+                            s_pv[j * 256 + threadIdx.x] = 0; // "empty": the deferred compare sends it on
                         }
                         s_ps[j * 256 + threadIdx.x] = hit;
                     }
@@ -1768,6 +1762,11 @@ DevSearch dev_search(const pg_ctx *ctx)
     d.DL = s->DL;
     d.nb = s->nb;
     d.gs = s->gs;
+    {
+        int lines_lg = 0;
+        while ((1ull << (lines_lg + 1)) <= (s->dir_slots >> (s->keyw == 1 ? 4 : 3))) lines_lg++;
+        d.hshift = 32 - std::min(lines_lg, 32); // dir_slots <= 2^25: at most 2^22 lines
+    }
     {
         unsigned __int128 low = 0, line = 0;
         for (int i = 0; i < s->D; i++) low |= (unsigned __int128)1 << (i * ctx->dp.key_bits);
