@@ -30,6 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG", "WARN")  # default only: the driver may ask for INFO to check the ranks
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own lines go to stderr: stdout carries the one JSON line
 
 import numpy as np  # noqa: E402
 
@@ -265,72 +266,105 @@ def run_ours(args, rank, world):
         G.search_end()
     else:
         from mpi_pastar_msa_b200.dist import CudaEngine, CudaEngineP2P, PartitionedSearch
-        G.configure_hash("FZORDER", args.hash_shift)
-        try:  # fused expansion + exchange over peer-mapped inboxes; NCCL all-to-all if symmetric memory is unavailable
-            if os.environ.get("PG_P2P", "1") == "0":
-                raise RuntimeError("PG_P2P=0")
-            fwd = os.environ.get("PG_FWD", "1") == "1"
-            eng = CudaEngineP2P(G, world, rank, dist, cap, batch, forward=fwd)
-            extra["exchange"] = ("device-driven parent forwarding: the claim kernel stores each live parent into the peer-mapped inbox (NVLink) of "
-                                 "every partition owning one of its successors; counts published by a device kernel, one symmetric-memory barrier per round"
-                                 if fwd else
-                                 "device-driven: p2p stores of successor records into peer-mapped inboxes (NVLink) from the expand kernel, counts "
-                                 "published by a device kernel, one symmetric-memory barrier per round")
-        except Exception as ex:
-            eng = CudaEngine(G, world, rank, cap, batch)
-            extra["exchange"] = "nccl all_to_all_single (p2p unavailable: %r)" % (ex,)
-        drv = PartitionedSearch(eng, dist, seqs, lambda pos: int(G.owner(np.array(pos, dtype=np.uint16), world)[0]))
-        if isinstance(eng, CudaEngineP2P) and eng.forward:
+        fwd = os.environ.get("PG_FWD", "1") == "1"
+
+        def make_engine(gpu, hash_type, hash_shift):
+            gpu.configure_hash(hash_type, hash_shift)
+            try:  # fused expansion + exchange over peer-mapped inboxes; NCCL all-to-all if symmetric memory is unavailable
+                if os.environ.get("PG_P2P", "1") == "0":
+                    raise RuntimeError("PG_P2P=0")
+                e = CudaEngineP2P(gpu, world, rank, dist, cap, batch, forward=fwd)
+                how = ("device-driven parent forwarding: the claim kernel stores each live parent into the peer-mapped inbox (NVLink) of "
+                       "every partition owning one of its successors; counts published by a device kernel, one symmetric-memory barrier per round"
+                       if fwd else
+                       "device-driven: p2p stores of successor records into peer-mapped inboxes (NVLink) from the expand kernel, counts "
+                       "published by a device kernel, one symmetric-memory barrier per round")
+            except Exception as ex:
+                e = CudaEngine(gpu, world, rank, cap, batch)
+                how = "nccl all_to_all_single (p2p unavailable: %r)" % (ex,)
+            return e, how
+
+        def timed_partitioned(gpu, hash_type, hash_shift, k_steps, w_steps, sample_clocks):
+            """Ramp the partitioned search up from the start node (untimed), then time k_steps rounds on the device."""
+            e, how = make_engine(gpu, hash_type, hash_shift)
+            dr = PartitionedSearch(e, dist, seqs, lambda pos: int(gpu.owner(np.array(pos, dtype=np.uint16), world)[0]))
+            ch = getattr(e, "async_rounds", False)  # device-driven rounds: one status exchange per call, not per round
+            rmp = 0
+            while True:
+                _, _, t0_ = dr.step(rounds=8 if ch else 1)
+                _, _, t1_ = dr.step(rounds=8 if ch else 1)
+                rmp += 16 if ch else 2
+                if t1_[2] - t0_[2] >= (8 if ch else 1) * world * batch or rmp > 4000:
+                    break
+            dr.step(rounds=w_steps)
+            _, _, t0_ = dr.step()
+            gpu.search_profile(True)
+            p0 = gpu.search_status()[2]
+            smp = ClockSampler(local) if sample_clocks else None
+            if smp:
+                smp.start()
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0 = dr.bytes_sent
+            ev0.record(stream)
+            if ch:
+                _, _, t1_ = dr.step(rounds=k_steps)
+            else:
+                for _ in range(k_steps):
+                    _, _, t1_ = dr.step()
+            ev1.record(stream)
+            barrier()
+            if smp:
+                smp.stop_flag = True
+            tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            p1 = gpu.search_status()[2]
+            gpu.search_profile(False)
+            out = {"max_ms": float(tt.item()), "tot0": t0_, "tot1": t1_, "ramp": rmp, "how": how, "sampler": smp,
+                   "nvlink_bytes_per_step_per_gpu": (dr.bytes_sent - s0) / k_steps,
+                   "rank0_kernel_ms_per_step": {k: (p1[k] - p0[k]) / k_steps for k in ("select_ms", "claim_ms", "expand_ms", "insert_ms", "inbox_ms")},
+                   "rank0_records_inserted_per_step": (p1["survivors"] - p0["survivors"]) / k_steps,
+                   "forward": isinstance(e, CudaEngineP2P) and e.forward, "p2p": isinstance(e, CudaEngineP2P)}
+            e.end()
+            return out
+
+        r_main = timed_partitioned(G, args.hash_type, args.hash_shift, K, W, True)
+        extra["exchange"] = r_main["how"]
+        if r_main["forward"]:
             launches_per_step = 7  # select, claim, forward, publish counts, expand (own), expand (forwarded), insert
-        elif isinstance(eng, CudaEngineP2P):
+        elif r_main["p2p"]:
             launches_per_step = 5 + (world - 1)  # select, claim, expand/probe, insert (local), publish counts + one insert per source
         else:
             launches_per_step = 6  # select, claim, expand/probe, insert (local), insert (received), status select
-        chained = getattr(eng, "async_rounds", False)  # device-driven rounds: one status exchange per call, not per round
-        ramp = 0
-        while True:
-            _, _, tot0 = drv.step(rounds=8 if chained else 1)
-            _, _, tot1 = drv.step(rounds=8 if chained else 1)
-            ramp += 16 if chained else 2
-            if tot1[2] - tot0[2] >= (8 if chained else 1) * world * batch or ramp > 4000:
-                break
-        drv.step(rounds=W)
-        _, _, tot0 = drv.step()
-        G.search_profile(True)
-        pc0 = G.search_status()[2]
-        sampler = ClockSampler(local)
-        sampler.start()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sent0 = drv.bytes_sent
-        e0.record(stream)
-        if chained:
-            _, _, tot1 = drv.step(rounds=K)
-        else:
-            for _ in range(K):
-                _, _, tot1 = drv.step()
-        e1.record(stream)
-        barrier()
-        sampler.stop_flag = True
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        max_ms = float(t.item())
+        ramp, sampler, max_ms = r_main["ramp"], r_main["sampler"], r_main["max_ms"]
+        tot0, tot1 = r_main["tot0"], r_main["tot1"]
         total_exp = tot1[0] - tot0[0]
         d = {"expansions": total_exp, "generated": tot1[1] - tot0[1], "pops": tot1[2] - tot0[2]}
-        extra["nvlink_bytes_per_step_per_gpu"] = (drv.bytes_sent - sent0) / K
-        pc1 = G.search_status()[2]
-        G.search_profile(False)
-        extra["rank0_kernel_ms_per_step"] = {k: (pc1[k] - pc0[k]) / K for k in ("select_ms", "claim_ms", "expand_ms", "insert_ms", "inbox_ms")}
-        extra["rank0_records_inserted_per_step"] = (pc1["survivors"] - pc0["survivors"]) / K
+        for k in ("nvlink_bytes_per_step_per_gpu", "rank0_kernel_ms_per_step", "rank0_records_inserted_per_step"):
+            extra[k] = r_main[k]
         expand_ms = select_ms = None
-        eng.end()
+        # the same measurement under the reference's default owner hash (FZORDER shift 12, CoordHash.cpp:17-18) and the
+        # round-1 setting (FZORDER shift 17), shorter: the owner hash decides how many parents straddle partitions
+        if not args.no_hash_sweep:
+            sweep = {}
+            for ht, sh in (("FZORDER", 12), ("FZORDER", 17)):
+                if (ht, sh) == (args.hash_type, args.hash_shift):
+                    continue
+                try:
+                    rs = timed_partitioned(G, ht, sh, max(5, K // 4), W, False)
+                    ex_ = rs["tot1"][0] - rs["tot0"][0]
+                    sweep["%s shift %d" % (ht, sh)] = {"value": ex_ / (rs["max_ms"] * 1e-3), "unit": UNIT, "ms_per_step": rs["max_ms"] / max(5, K // 4),
+                                                       "steps": max(5, K // 4), "nvlink_bytes_per_step_per_gpu": rs["nvlink_bytes_per_step_per_gpu"],
+                                                       "rank0_kernel_ms_per_step": rs["rank0_kernel_ms_per_step"]}
+                except Exception as ex:
+                    sweep["%s shift %d" % (ht, sh)] = {"error": repr(ex)}
+            extra["owner_hash_sweep"] = sweep
 
     value = total_exp / (max_ms * 1e-3)
     clocks = sampler.result()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "table_slots_per_gpu": cap, "parallelism": "hash-partition x%d" % world + ("" if world == 1 else " (FZORDER shift %d)" % args.hash_shift),
+            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "table_slots_per_gpu": cap, "parallelism": "hash-partition x%d" % world + ("" if world == 1 else " (%s shift %d)" % (args.hash_type, args.hash_shift)),
                        "ramp_up_rounds_untimed": ramp,
                        "l2": "inputs larger than L2: %.1f GiB hash table per GPU, ~%d MB of distinct sectors touched per step"
                              % (cap * 16 / 2**30, batch * 127 * 32 // 10**6)},
@@ -505,8 +539,7 @@ def run_ours(args, rank, world):
         G2 = m.PastarGPU(seqs, device=local)
         G2.set_stream(stream.cuda_stream)
         G2.build_pair_tables()
-        G2.configure_hash("FZORDER", args.hash_shift)
-        eng2 = CudaEngineP2P(G2, world, rank, dist, cap, batch, forward=fwd) if isinstance(eng, CudaEngineP2P) else CudaEngine(G2, world, rank, cap, batch)
+        eng2, _ = make_engine(G2, args.hash_type, args.hash_shift)
         drv2 = PartitionedSearch(eng2, dist, seqs, lambda pos: int(G2.owner(np.array(pos, dtype=np.uint16), world)[0]), max_expansions=budget)
         drv2.rounds_per_status = 8
         r = drv2.run()
@@ -544,8 +577,13 @@ def main():
     ap.add_argument("--table-capacity", type=int, default=1 << 30)
     ap.add_argument("--quick", action="store_true", help="N = 1: print the round's timing only (no extras, e2e or CPU baseline)")
     ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the untimed PF08184 / kinase parity gate (profiling runs)")
-    ap.add_argument("--hash-shift", type=int, default=17,
-                    help="FZORDER owner-hash shift for N > 1 (the reference's -s, 0..21; its default 12 puts owner bits at bit 1 of two coordinates, 17 at bit 2 of three: fewer parents straddle partitions)")
+    ap.add_argument("--hash-type", default="PZORDER", choices=["FZORDER", "PZORDER", "FSUM", "PSUM"],
+                    help="owner hash for N > 1 (the reference's -y; its default FZORDER shift 12 is reported in extra.owner_hash_sweep)")
+    ap.add_argument("--hash-shift", type=int, default=6,
+                    help="owner-hash shift for N > 1 (the reference's -s, 0..21).  PZORDER shift 6 takes bits 3-4 of the first two "
+                         "coordinates: an eighth of the parents straddle a partition boundary per owner coordinate; FZORDER shift 12 "
+                         "(bit 1 of five coordinates) makes most parents straddle several")
+    ap.add_argument("--no-hash-sweep", action="store_true", help="N > 1: skip the FZORDER shift 12 / 17 comparison runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

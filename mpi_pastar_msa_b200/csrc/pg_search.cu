@@ -81,6 +81,8 @@ struct SearchState {
     uint32_t *d_hint = nullptr;
     uint32_t *d_pool = nullptr;
     unsigned long long *d_link = nullptr;    // per unit: {offset, lg} of the previous chunk of the bucket
+    uint32_t *d_free = nullptr;              // free stacks of popped chunks, one per size class
+    uint32_t free_off[16] = {0};             // first entry of class lg's stack in d_free
     uint32_t n_units = 0;
     PlanEntry *d_plan = nullptr;
     uint32_t plan_cap = 0;
@@ -233,6 +235,8 @@ struct DevSearch {
     uint32_t *hint; // per bucket: log2 units of the largest chunk it ever had
     uint32_t *pool;
     unsigned long long *link;
+    uint32_t *free_stack;  // chunks popped empty by select, per size class lg at free_stack + free_off[lg]; count in ctrl->free_top[lg]
+    uint32_t free_off[16];
     uint32_t n_units;
     unsigned long long goal_lo, goal_hi;
     PlanEntry *plan;
@@ -439,11 +443,20 @@ __device__ __noinline__ void bucket_place_slow(const DevSearch &d, int b, uint32
             // not re-grown 64, 128, ... every round.  Pushers that lost the race poll until the new head is published,
             // so the critical section is only bump + publish; bookkeeping that only the select kernel reads comes after.
             const uint32_t nlg = off == CHUNK_NONE ? min(d.hint[b], MAXLG) : min(lg + 1u, MAXLG);
-            const uint32_t nc = atomicAdd(&c->chunk_bump, 1u << nlg);
-            if ((unsigned long long)nc + (1u << nlg) > d.n_units) {
-                c->error = 2;
-                atomicExch(bk, bucket_pack(off, lg, capn)); // leave the bucket consistent
-                return;
+            // a chunk the select kernel popped empty (this round's claim kernel has read it: inserts run after it), else fresh
+            // pool space.  Pops only race with pops (select, the only pusher, never runs beside an insert kernel).
+            uint32_t nc;
+            const int ft = atomicSub(&c->free_top[nlg], 1) - 1;
+            if (ft >= 0) {
+                nc = d.free_stack[d.free_off[nlg] + ft];
+            } else {
+                atomicAdd(&c->free_top[nlg], 1);
+                nc = atomicAdd(&c->chunk_bump, 1u << nlg);
+                if ((unsigned long long)nc + (1u << nlg) > d.n_units) {
+                    c->error = 2;
+                    atomicExch(bk, bucket_pack(off, lg, capn)); // leave the bucket consistent
+                    return;
+                }
             }
             atomicExch(bk, bucket_pack(nc, nlg, 1u));
             d.link[nc] = ((unsigned long long)off << 32) | lg;
@@ -640,6 +653,10 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(DevSearch d, lon
             e_off += n;
             left -= n;
             remain -= n;
+            if (n == fill) { // popped empty: the bucket lets go of it; recycled by this round's inserts (after the claim kernel)
+                const int ft = atomicAdd(&c->free_top[chlg], 1);
+                d.free_stack[d.free_off[chlg] + ft] = ch;
+            }
             if (n < fill || remain == 0) { // this chunk keeps fill-n entries and stays the head
                 fill -= n;
                 break;
@@ -1081,6 +1098,32 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     const unsigned fmask = (1u << p.key_bits) - 1u;
     const int full = (1 << N) - 1;
 
+    // ---- owner hash, split into what is fixed for the kernel, per lane, and per parent.  Z-order hashes: bit m of
+    // the owner word is bit oa.bit[m] of coordinate oa.co[m].  lanemask = the word bits whose coordinate this LANE moves,
+    // hmask[b] = the word bits of the coordinate the b-th loop bit moves.  Sum hashes: the successor's sum is the parent's
+    // plus the number of moved sequences among the first nd.
+    unsigned lanemask = 0, hmask[C::HB > 0 ? C::HB : 1];
+#pragma unroll
+    for (int b = 0; b < C::HB; b++) hmask[b] = 0;
+    const bool zorder = oa.type != PG_HASH_FSUM && oa.type != PG_HASH_PSUM;
+    const int sum_nd = oa.type == PG_HASH_PSUM ? 2 : N;
+    const int ksub = __popc(sub & ((1 << sum_nd) - 1)); // sum hashes: sequences this lane moves (N >= 3 > 2: PSUM is lane-uniform)
+    if constexpr (MULTI) {
+        if (zorder) {
+            for (int m = 0; m < oa.nb; m++) {
+                const int co = oa.co[m];
+                if (co < 0) continue;
+                if (co < C::A) {
+                    if ((sub >> co) & 1) lanemask |= 1u << m;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < C::HB; b++)
+                        if (co - C::A == b) hmask[b] |= 1u << m;
+                }
+            }
+        }
+    }
+
     // ---- the deferred half of a probe batch: compare the values that have arrived; stage the survivors
     bool pend = false;          // warp-uniform
     unsigned pend_vmask = 0;    // which of the batch's PF probes this lane issued
@@ -1167,28 +1210,45 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                 pg_expand_prepare<N>(p, meta, s_grp, pos, g, parenti, sub, gmask, L);
             }
         }
-        unsigned wbase = 0;
+        unsigned wbase = 0, wany = 0;
         unsigned wflip[C::HB > 0 ? C::HB : 1];
 #pragma unroll
         for (int b = 0; b < C::HB; b++) wflip[b] = 0;
+        int qmod = 0, rk = 0; // sum hashes: (parent sum >> shift) % n_parts, low part of the sum + this lane's moves
+        bool uniform = false; // one owner for all of this lane's successors
         if constexpr (MULTI) {
-            if (oa.type != PG_HASH_FSUM && oa.type != PG_HASH_PSUM) {
+            if (zorder) {
+                unsigned w0 = 0, w1 = 0; // owner word with no / every owner coordinate advanced
                 for (int m = 0; m < oa.nb; m++) {
                     const int co = oa.co[m];
                     if (co < 0) continue;
                     const unsigned pc = pkey.field(co * p.key_bits, fmask);
-                    const unsigned v0 = (pc >> oa.bit[m]) & 1u, v1 = ((pc + 1u) >> oa.bit[m]) & 1u;
-                    if (co < C::A) {
-                        wbase |= (((sub >> co) & 1) ? v1 : v0) << m;
-                    } else {
-                        wbase |= v0 << m;
-#pragma unroll
-                        for (int b = 0; b < C::HB; b++)
-                            if (co - C::A == b) wflip[b] |= (v0 ^ v1) << m;
-                    }
+                    w0 |= ((pc >> oa.bit[m]) & 1u) << m;
+                    w1 |= (((pc + 1u) >> oa.bit[m]) & 1u) << m;
                 }
+                wbase = (w0 & ~lanemask) | (w1 & lanemask);
+#pragma unroll
+                for (int b = 0; b < C::HB; b++) {
+                    wflip[b] = (w0 ^ w1) & hmask[b];
+                    wany |= wflip[b];
+                }
+                uniform = wany == 0; // most parents lie inside one partition's cell in every loop coordinate
+            } else {
+                unsigned psum = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++)
+                    if (i < sum_nd) psum += act ? (unsigned)pos[i] : 0u;
+                qmod = (int)((psum >> oa.shift) % (unsigned)d.n_parts);
+                rk = (int)(psum & ((1u << oa.shift) - 1u)) + ksub;
+                const int kmax = sum_nd > C::A ? sum_nd - C::A : 0; // loop bits that count towards the sum
+                uniform = ((unsigned)rk >> oa.shift) == ((unsigned)(rk + kmax) >> oa.shift);
+                wbase = (unsigned)qmod + ((unsigned)rk >> oa.shift); // < 64 + 17: s_mod reduces it
             }
         }
+        const int lown = uniform ? (int)s_mod[wbase] : d.part;
+        const bool own_all = uniform && lown == d.part;
+        const bool own_none = MODE == 2 && uniform && lown != d.part;
+        const bool lane_foreign = SEND && act && uniform && lown != d.part; // MODE 1: the lane's whole batch goes to partition lown
         PH_MARK(2); // prepare (LUT gathers, HH, B/E)
         Key<KEYW> klow = pkey;
 #pragma unroll
@@ -1215,6 +1275,28 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                 // the previous batch (of this parent, or the last one of the previous parent: its value loads travelled
                 // while this parent's LUTs were staged) is compared before its stash is reused
                 if (pend) complete();
+                // MODE 1, lane-uniform owner: the lanes of a warp that send to the same partition reserve their PF record
+                // slots each with ONE atomic on that destination's counter; a lane then stores its records (a hole for
+                // a successor that does not exist or is pruned) straight into the owner's inbox while it computes
+                unsigned long long *obase = nullptr;
+                if constexpr (SEND) {
+                    const unsigned fl = __ballot_sync(0xffffffffu, lane_foreign);
+                    if (lane_foreign) {
+                        const unsigned grp = __match_any_sync(fl, lown);
+                        const int leader = __ffs(grp) - 1;
+                        const unsigned long long k = (unsigned long long)__popc(grp) * PF;
+                        unsigned long long b0 = 0;
+                        if (lane == leader) {
+                            b0 = atomicAdd(&d.outbox_count[lown], k);
+                            if (b0 + k > d.outbox_cap) {
+                                c->error = 4;
+                                b0 = 0; // keep writes in bounds; the run is abandoned with PG_ERR_CAPACITY
+                            }
+                        }
+                        b0 = __shfl_sync(grp, b0, leader);
+                        obase = outbox_record<KEYW>(d, lown, b0 + (unsigned long long)__popc(grp & lt) * PF);
+                    }
+                }
                 unsigned long long h0[PF], h1[KEYW == 2 ? PF : 1]; // directory words
                 uint32_t ls[PF];                                     // directory slots
                 unsigned vmask = 0;
@@ -1231,14 +1313,13 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     if constexpr (KEYW == 2) h1[j] = 0;
                     ls[j] = 0;
                     int own = d.part;
+                    if constexpr (MODE == 2) v = v && !own_none;
                     if constexpr (MULTI) {
-                        if (v) {
-                            if (oa.type == PG_HASH_FSUM || oa.type == PG_HASH_PSUM) {
-                                const Key<KEYW> key = klow.plus(s_keyhigh[high]);
-                                unsigned sm = 0;
-                                const int nd = oa.type == PG_HASH_PSUM ? 2 : N;
-                                for (int q = 0; q < nd; q++) sm += key.field(q * p.key_bits, fmask);
-                                own = (int)((sm >> oa.shift) % (unsigned)d.n_parts);
+                        if (v && !own_all && !lane_foreign) {
+                            if (!zorder) {
+                                // the successor's sum is the parent's plus the sequences moved: (sum >> shift) % n_parts
+                                const int kh = sum_nd > C::A ? __popc((unsigned)high & ((1u << (sum_nd - C::A)) - 1u)) : 0;
+                                own = (int)s_mod[(unsigned)qmod + ((unsigned)(rk + kh) >> oa.shift)];
                             } else {
                                 // the owner word of a successor differs from wbase (this lane, no high move) only in the
                                 // bits tied to the high coordinates that move: one XOR per moved coordinate
@@ -1266,6 +1347,17 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                         }
                         if (drop) {
                             n_pruned++;
+                            v = false;
+                        }
+                    }
+                    if constexpr (SEND) {
+                        if (obase) { // lane-uniform owner elsewhere: record j of this lane's reservation (move mask 0 = hole)
+                            unsigned long long *r = obase + j * XW;
+                            const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                            r[0] = key.lo;
+                            if constexpr (KEYW == 2) r[1] = key.hi;
+                            r[KEYW] = ((unsigned long long)(unsigned)gn << 32) | (unsigned)fn;
+                            r[KEYW + 1] = v ? (unsigned long long)(unsigned)mask : 0ull;
                             v = false;
                         }
                     }
@@ -1782,6 +1874,8 @@ DevSearch dev_search(const pg_ctx *ctx)
     d.hint = s->d_hint;
     d.pool = s->d_pool;
     d.link = s->d_link;
+    d.free_stack = s->d_free;
+    for (int i = 0; i < 16; i++) d.free_off[i] = s->free_off[i];
     d.n_units = s->n_units;
     {   // packed key of the final coordinate (Sequences::get_final_coord, Sequences.cpp:53-60)
         unsigned __int128 k = 0;
@@ -2080,6 +2174,7 @@ void pg_search_free(pg_ctx *ctx)
     cudaFree(s->d_hint);
     cudaFree(s->d_pool);
     cudaFree(s->d_link);
+    cudaFree(s->d_free);
     cudaFree(s->d_plan);
     cudaFree(s->d_ctrl);
     cudaFree(s->d_trace);
@@ -2197,6 +2292,14 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     s->n_units = (uint32_t)std::min<uint64_t>(units, 0x7ffffff0ull);
     PG_CUDA(ctx, cudaMalloc(&s->d_pool, (size_t)s->n_units * UNIT * 4));
     PG_CUDA(ctx, cudaMalloc(&s->d_link, (size_t)s->n_units * 8));
+    {   // free stacks: class lg can never hold more than n_units >> lg chunks
+        uint32_t tot = 0;
+        for (uint32_t lg = 0; lg <= MAXLG; lg++) {
+            s->free_off[lg] = tot;
+            tot += (s->n_units >> lg) + 1;
+        }
+        PG_CUDA(ctx, cudaMalloc(&s->d_free, (size_t)tot * 4));
+    }
     // a round pops at most ~2*target entries: the bucket crossing the target may add one chunk of up to the
     // entries already taken.  Plan entries: one per chunk.
     s->plan_cap = (uint32_t)(SELECT_THREADS * (MAXLG + 4) + 64);

@@ -1,6 +1,6 @@
 """python tools/print_bench.py bench.json : the few numbers of a bench.py line one looks at first."""
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
 print("%d GPU(s): %.1f M expansions/s, %.3f ms/round, e2e %.1f M/s" % (d["n_gpus"], d["value"] / 1e6, d["ms_per_step"], ((d.get("e2e") or {}).get("value") or 0) / 1e6))
 r = d.get("roofline")
 if r:
