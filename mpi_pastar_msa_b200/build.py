@@ -81,6 +81,11 @@ def build(force=False, verbose=False, ptxas_info=False):
     if cli and not VARIANT and (force or _newer(cli + hdrs + [LIB], BIN)):
         _run([CXX] + CXX_FLAGS + cli + ["-o", BIN, "-L" + os.path.dirname(LIB), "-lpastar_gpu", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"],
              verbose)
+    # the C++ boundary test program (tests/cpp/boundary_test.cpp): binds the host mirror's Node / Coord / HeuristicHPair
+    tsrc = os.path.join(ROOT, "tests", "cpp", "boundary_test.cpp")
+    tbin = os.path.join(HERE, "bin", "boundary_test")
+    if os.path.exists(tsrc) and not VARIANT and (force or _newer([tsrc] + hdrs + [LIB], tbin)):
+        _run([CXX] + CXX_FLAGS + [tsrc, "-o", tbin, "-L" + os.path.dirname(LIB), "-lpastar_gpu", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"], verbose)
     return LIB
 
 
