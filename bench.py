@@ -123,6 +123,19 @@ def cpu_reference_run(threads, steps, warmup, want_sample=True):
             "seconds": secs, "expansions": exps}
 
 
+def probe_reference_toolchain():
+    """can the real reference (mpich + Boost + LZ4, `make` -> ./bin/pastar) be built on this box?  Its
+    sources are not on the GPU box (/root/reference exists only in the build container), so even a complete toolchain could
+    only build it there; recorded so that the baseline's kind is never a guess."""
+    import shutil
+    have = {"mpicxx": bool(shutil.which("mpicxx") or shutil.which("mpic++")), "mpiexec": bool(shutil.which("mpiexec")),
+            "boost_headers": any(os.path.exists(os.path.join(d, "boost", "multi_index_container.hpp")) for d in ("/usr/include", "/usr/local/include")),
+            "lz4_header": any(os.path.exists(os.path.join(d, "lz4.h")) for d in ("/usr/include", "/usr/local/include")),
+            "reference_sources": os.path.exists("/root/reference/pastar/PAStar.cpp")}
+    have["buildable"] = all(have.values())
+    return have
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -137,7 +150,7 @@ def run_reference(args, rank, world):
                        "nproc": os.cpu_count()},
             "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.time() - t0}
+            "gpu_launches": 0, "wall_s": time.time() - t0, "reference_build": probe_reference_toolchain()}
     print(json.dumps(line), flush=True)
 
 
@@ -366,8 +379,8 @@ def run_ours(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "table_slots_per_gpu": cap, "parallelism": "hash-partition x%d" % world + ("" if world == 1 else " (%s shift %d)" % (args.hash_type, args.hash_shift)),
                        "ramp_up_rounds_untimed": ramp,
-                       "l2": "inputs larger than L2: %.1f GiB hash table per GPU, ~%d MB of distinct sectors touched per step"
-                             % (cap * 16 / 2**30, batch * 127 * 32 // 10**6)},
+                       "l2": "inputs larger than L2: %.1f GiB of value blocks per GPU (4 four-byte slots per coordinate), ~1 GB of distinct 128-byte lines touched per step"
+                             % (cap * 16 / 2**30)},
             "clocks": clocks, "gpu_launches": launches_per_step * K,
             "successors_per_sec": d["generated"] / (max_ms * 1e-3)}
 
@@ -383,9 +396,9 @@ def run_ours(args, rank, world):
         n_surv = surv if surv else d["pushed"]  # lower bound when the library does not count survivors
         kern = {
             "select_kernel": (select_ms, 0.0),
-            "claim_kernel": (claim_ms, d["pops"] * 20.0 + d["expansions"] * 16.0),
-            "expand_probe_kernel<7,1,false>": (expand_ms, d["expansions"] * (16.0 + n + 16 * P) + d["probed"] * 32.0 + n_surv * 24.0),
-            "insert_kernel<1>": (insert_ms, n_surv * 56.0 + d["pushed"] * 36.0),
+            "claim_kernel<1,4>": (claim_ms, d["pops"] * 20.0 + d["expansions"] * 16.0),
+            "expand_probe_kernel<7,1,4,0>": (expand_ms, d["expansions"] * (16.0 + n + 16 * P) + d["probed"] * 32.0 + n_surv * 24.0),
+            "insert_kernel<1,4>": (insert_ms, n_surv * 56.0 + d["pushed"] * 36.0),
         }
         allk = {}
         for name, (kms, alg) in kern.items():
@@ -399,10 +412,14 @@ def run_ours(args, rank, world):
                             "avg_launch_us": 1e3 * tms / K, "algorithmic_bytes_per_launch": alg / K,
                             "share_of_step": tms / ms, "kernels": allk,
                             "whole_round_frac": sum(v[1] for v in kern.values()) / (ms * 1e-3) / 1e9 / hbm}
-        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        # DRAM bytes per launch of the same kernel from one `ncu --set full` capture of this workload (tools/ncu_round.sh;
+        # summaries under profiles/): null when no capture of the current kernel is recorded
+        tr = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tr):
             try:
-                line["roofline"]["traffic"] = json.load(open(tr)).get(top)
+                t_ = json.load(open(tr))
+                line["roofline"]["traffic"] = t_["kernels"].get(top.split("<")[0])
+                line["roofline"]["traffic_source"] = t_.get("source")
             except Exception:
                 pass
         if args.quick:  # kernel-tuning runs: the round's timing only
@@ -443,18 +460,18 @@ def run_ours(args, rank, world):
         except Exception as ex:
             extra["gather_roofline"] = {"error": repr(ex)}
         # integer peak for the DP, two ways: (a) measured - a kernel that issues only the DP cell's own arithmetic (3 adds +
-        # min3, 8 independent chains per thread) on every SM; (b) nominal lanes x clock at the 26 thread instructions per
+        # min3, 8 independent chains per thread) on every SM; (b) nominal lanes x clock at the 8 thread instructions per
         # cell the DP kernel actually executes (staging, shuffles, stores included)
         try:
             cell_peak_gcups = m.bench_int_peak(local) / 1e9
         except Exception:
             cell_peak_gcups = None
-        int_peak_gcups = 148 * 128 * (clocks.get("sm_mhz") or 1965) * 1e6 / 26 / 1e9
+        int_peak_gcups = 148 * 128 * (clocks.get("sm_mhz") or 1965) * 1e6 / 8 / 1e9  # linear-gap kernel: ~118 warp instructions per 16-cell block + staging
         extra["pair_dp"] = {"kernel": "pair_dp_kernel", "cells": cells, "ms": dp_ms, "gcups": cells / (dp_ms * 1e-3) / 1e9,
                             "frac_of_integer_peak": cells / (dp_ms * 1e-3) / 1e9 / int_peak_gcups,
                             "integer_peak_gcups": int_peak_gcups, "measured_cell_arithmetic_peak_gcups": cell_peak_gcups,
                             "frac_of_measured_cell_peak": (cells / (dp_ms * 1e-3) / 1e9 / cell_peak_gcups) if cell_peak_gcups else None,
-                            "note": "one CTA per pair: 21 of 148 SMs busy"}
+                            "note": "latency-bound wavefront, one CTA per pair: 21 of 148 SMs busy; bound by the L1 + L2 - 1 anti-diagonal steps, not by the integer pipes"}
         # ---- BASELINE configs[4]: synthetic 8 x 1000 - the 28-table heuristic build and the batched expansion at N = 8
         try:
             import random
@@ -520,6 +537,41 @@ def run_ours(args, rank, world):
                        "wall_s": wall, "context_s": t_ctx, "search_kernel_s": r["kernel_ms"] * 1e-3,
                        "includes": "host Altschul weights, context create, pairwise DP, table allocation + clear, search from the start node "
                                    "(%.1fx the expansions of the timed arm's whole run), result read-back" % factor}
+        # ---- a TERMINATING anchor: kinase.fasta (BASELINE configs[1]) solved to the optimality-preserving stop, on the device
+        # and end to end from host buffers; expansions raw and "useful" (no more than the serial A* needs: batching expands
+        # nodes a serial search never would)
+        try:
+            kseqs = PARITY_INPUTS["kinase"][0]
+            t0 = time.perf_counter()
+            Gk = m.PastarGPU(kseqs, device=local)
+            Gk.build_pair_tables()
+            rk = Gk.search(table_capacity=1 << 26, batch_target=16384, want_rows=True)
+            torch.cuda.synchronize()
+            wall_k = time.perf_counter() - t0
+            ok_k = rk["finished"] == 1 and rk["g"] == 421546 and m.rescore_alignment(kseqs, Gk.w_int, rk["rows"]) == 421546
+            Gk.close()
+            serial = 4497278  # expansions of the serial A* on the reference's arithmetic (oracle/_ref astar; tie-break dependent)
+            extra["kinase"] = {"workload": "kinase.fasta (5 x 263-276) full solve, batch 16384", "optimal_cost": rk["g"], "parity": "ok" if ok_k else "FAILED",
+                               "expansions_raw": rk["expansions"], "expansions_useful": min(rk["expansions"], serial), "serial_astar_expansions": serial,
+                               "rounds": rk["rounds"], "device_ms": rk["kernel_ms"], "value_expansions_per_sec": rk["expansions"] / (rk["kernel_ms"] * 1e-3),
+                               "useful_expansions_per_sec": min(rk["expansions"], serial) / (rk["kernel_ms"] * 1e-3),
+                               "e2e_wall_s": wall_k, "e2e_expansions_per_sec": rk["expansions"] / wall_k,
+                               "cpu_reference_full_solve": {"seconds": 398.0, "threads": 1, "what": "oracle/_ref serial A* (AStar.cpp:53-104 semantics) on the survey container, recorded in DESIGN.md; not re-run here (bounded bench)"}}
+            if not ok_k:
+                raise SystemExit("kinase.fasta: optimal cost / alignment mismatch")
+            try:  # the CPU path on the same input, bounded to ~10 s
+                from oracle import refio
+                if refio.available():
+                    threads = os.cpu_count() or 1
+                    rc_ = refio.pastar(kseqs, threads, 400000, "FZORDER", 12, timeout=600, warm_pops=20000)
+                    extra["kinase"]["cpu_reference_sample"] = {"expansions_per_sec": rc_["timed_expansions"] / rc_["timed_seconds"], "threads": threads,
+                                                               "dequeues": 400000, "kind": "reference"}
+            except Exception as ex:
+                extra["kinase"]["cpu_reference_sample"] = {"error": repr(ex)}
+        except SystemExit:
+            raise
+        except Exception as ex:
+            extra["kinase"] = {"error": repr(ex)}
         # ---- CPU baseline beside it (bounded sample)
         try:
             threads = os.cpu_count() or 1
