@@ -67,6 +67,13 @@ void pg_default_cost_table(int32_t out90x90[90 * 90]);
  * overflow at L >= 999) any length is accepted. */
 int pg_host_weights(int n_seq, const char *const *seqs, const int *lens, float *w_out);
 
+/* The same weights with the pair loop (the reference's `primer`: N(N-1)/2 three-matrix forward alignments and their
+ * tracebacks, pastar/WeightedSP.cpp:144-244, 109-142 - half of HeuristicHPair::init) run as ONE kernel on `device`
+ * (< 0: the current one); the neighbour-joining tree and the float propagation (WeightedSP.cpp:317-420, 464-509) stay on
+ * the host.  Output bit-identical to pg_host_weights.  kernel_ms (may be NULL) receives the kernel's CUDA-event time.
+ * PG_ERR_UNSUPPORTED when a sequence is too long for the shared-memory sweep (about 5 800 residues): use pg_host_weights. */
+int pg_gpu_weights(int n_seq, const char *const *seqs, const int *lens, int device, float *w_out, float *kernel_ms);
+
 /* ------------------------------------------------------------------ context */
 
 /* Replaces Sequences::set_seq + the Cost/HeuristicHPair singletons' state
@@ -76,6 +83,11 @@ int pg_host_weights(int n_seq, const char *const *seqs, const int *lens, float *
  * device < 0 keeps the current CUDA device. */
 int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens, const int32_t *cost90x90, int gap_open,
                   int gap_ext, int gap_gap, const int32_t *w_int, int device, pg_ctx **out);
+/* The reference instantiates its templates for N in {3..10, 14, 16} only (pastar/include/max_seq_helper.h:9-19) and
+ * pg_ctx_create follows it.  pg_allow_extended_n(1) - an explicit, process-wide opt-in that diverges from the reference -
+ * also admits N = 11, 12, 13, 15 (pairwise tables, weights, getNeigh batches and the one-GPU search; the partitioned
+ * search is not built for them and pg_search_begin refuses n_parts > 1). */
+int pg_allow_extended_n(int enable);
 void pg_ctx_destroy(pg_ctx *ctx);
 const char *pg_last_error(const pg_ctx *ctx);
 int pg_abi_version(void);

@@ -68,8 +68,10 @@ def load_library():
         "pg_last_error": ([vp], C.c_char_p),
         "pg_default_cost_table": ([vp], None),
         "pg_host_weights": ([i32, C.POINTER(C.c_char_p), C.POINTER(i32), vp], i32),
+        "pg_gpu_weights": ([i32, C.POINTER(C.c_char_p), C.POINTER(i32), i32, vp, C.POINTER(C.c_float)], i32),
         "pg_ctx_create": ([i32, C.POINTER(C.c_char_p), C.POINTER(i32), vp, i32, i32, i32, vp, i32, C.POINTER(vp)], i32),
         "pg_ctx_destroy": ([vp], None),
+        "pg_allow_extended_n": ([i32], i32),
         "pg_ctx_set_stream": ([vp, vp], i32),
         "pg_search_rounds": ([vp, C.c_int32, C.c_int32], i32),
         "pg_search_profile": ([vp, i32], i32),
@@ -111,7 +113,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_bench_int_peak", "pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_allow_extended_n", "pg_gpu_weights", "pg_bench_int_peak", "pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -237,6 +239,24 @@ def host_weights(seqs):
     return out
 
 
+def allow_extended_n(enable=True):
+    """Explicit opt-in (diverges from the reference, max_seq_helper.h:9-19): also accept N = 11, 12, 13, 15 on one GPU."""
+    load_library().pg_allow_extended_n(1 if enable else 0)
+
+
+def gpu_weights(seqs, device=-1, want_ms=False):
+    """weightAltschulsRationale2 with the pair loop (primer, WeightedSP.cpp:144-244) as one kernel: same floats as host_weights."""
+    L = load_library()
+    n = len(seqs)
+    keep = _seq_args(seqs)
+    out = np.zeros((n, n), dtype=np.float32)
+    ms = C.c_float(0)
+    rc = L.pg_gpu_weights(n, keep[1], keep[2], device, out.ctypes.data, C.byref(ms))
+    if rc:
+        raise PastarError(rc, "pg_gpu_weights failed")
+    return (out, ms.value) if want_ms else out
+
+
 class PastarGPU:
     """One problem (sequence set) on one GPU: the Sequences + Cost + HeuristicHPair singletons of the reference."""
 
@@ -247,8 +267,18 @@ class PastarGPU:
         self.lens = [len(s) for s in self.seqs]
         self.npairs = self.n * (self.n - 1) // 2
         self.S = (1 << self.n) - 1
-        if isinstance(weights, str) and weights == "altschul":
-            self.weights_f = host_weights(self.seqs)
+        if isinstance(weights, str) and weights in ("altschul", "altschul_host"):
+            # pair loop of the weight routine on the device (pg_gpu_weights); the host routine for sequences beyond its
+            # shared-memory sweep or on request - both give the reference's floats bit for bit
+            self.weights_f = None
+            if weights == "altschul":
+                try:
+                    self.weights_f = gpu_weights(self.seqs, device)
+                except PastarError as e:
+                    if e.code != 3:
+                        raise
+            if self.weights_f is None:
+                self.weights_f = host_weights(self.seqs)
             self.w_int = self.weights_f.astype(np.int32)  # (int) truncation, Node.cpp:226
         elif weights is None:
             self.weights_f, self.w_int = None, np.ones((self.n, self.n), dtype=np.int32)

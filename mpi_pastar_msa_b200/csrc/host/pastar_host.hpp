@@ -149,8 +149,10 @@ class HeuristicHPair {
             len[i] = (int)seq->get_seq(i).size();
         }
         flat.assign((size_t)n * n, 0.0f);
-        int rc = pg_host_weights(n, ptr.data(), len.data(), flat.data());
-        if (rc != PG_OK) throw GpuError(rc, "pg_host_weights failed");
+        // the pair loop of weightAltschulsRationale2 runs on the device; very long sequences take the host routine
+        int rc = pg_gpu_weights(n, ptr.data(), len.data(), device, flat.data(), nullptr);
+        if (rc == PG_ERR_UNSUPPORTED) rc = pg_host_weights(n, ptr.data(), len.data(), flat.data());
+        if (rc != PG_OK) throw GpuError(rc, "pair weights (pg_gpu_weights / pg_host_weights) failed");
         rows.resize(n);
         for (int i = 0; i < n; i++) rows[i] = flat.data() + (size_t)i * n;
         weightMatrix = rows.data();

@@ -74,6 +74,19 @@ const CostTable &cost_table()
 }
 
 inline int min3(int a, int b, int c) { return a < b ? (a < c ? a : c) : (b < c ? b : c); }
+} // namespace
+
+// identity-based distance x1000 of a pair from the number of identical columns on its alignment path
+// (primer's tail, WeightedSP.cpp:222-228); en / em = the two sequence lengths
+float pg_distance_from_matches(int en, int em, int match)
+{
+    const int scaled = (int)(0.5 + 1000.0 * (en - match + em - match) / (en + em));
+    const float d = (float)scaled;
+    return d <= 0 ? 1.0f : d; // WeightedSP.cpp:227-228
+}
+const int32_t *pg_cost_table_data();
+
+namespace {
 
 // Identity-based distance x1000 between two dash-prefixed strings (primer + convert_path_to_cost).
 float pair_distance(const std::string &sa, const std::string &sb)
@@ -125,9 +138,7 @@ float pair_distance(const std::string &sa, const std::string &sb)
             --j;
         }
     }
-    const int scaled = (int)(0.5 + 1000.0 * (en - match + em - match) / (en + em));
-    const float d = (float)scaled;
-    return d <= 0 ? 1.0f : d; // WeightedSP.cpp:227-228
+    return pg_distance_from_matches(en, em, match);
 }
 
 // Neighbour-joining tree in arrays.  kind: >= 0 leaf (sequence id), -1 internal, -2 root.
@@ -283,6 +294,9 @@ struct NJ {
 
 } // namespace
 
+const int32_t *pg_cost_table_data() { return cost_table().v; }
+int pg_weights_from_distances(int n, const std::vector<float> &dist, float *w_out);
+
 extern "C" void pg_default_cost_table(int32_t out90x90[90 * 90]) { memcpy(out90x90, cost_table().v, sizeof(int32_t) * 8100); }
 
 extern "C" int pg_host_weights(int n_seq, const char *const *seqs, const int *lens, float *w_out)
@@ -318,6 +332,13 @@ extern "C" int pg_host_weights(int n_seq, const char *const *seqs, const int *le
         for (std::thread &t : pool) t.join();
     }
 
+    return pg_weights_from_distances(n, dist, w_out);
+}
+
+// Neighbour-joining tree, partial weights, scaling (WeightedSP.cpp:317-420, 464-509) from the pair distances.  Shared by
+// the host producer above and by pg_gpu_weights, whose device kernel produces the distances' match counts.
+int pg_weights_from_distances(int n, const std::vector<float> &dist, float *w_out)
+{
     NJ nj(dist, n);
     nj.build();
     Tree &t = nj.t;

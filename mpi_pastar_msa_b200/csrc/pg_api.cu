@@ -151,9 +151,16 @@ int pg_stage(pg_ctx *ctx, int which, size_t bytes, void **out)
     return PG_OK;
 }
 
+static bool g_extended_n = false; // explicit opt-in, process-wide: sequence counts the reference cannot run
+extern "C" int pg_allow_extended_n(int enable)
+{
+    g_extended_n = enable != 0;
+    return PG_OK;
+}
 static bool supported_n(int n)
 {
-    return (n >= 3 && n <= 10) || n == 14 || n == 16; // max_seq_helper.h:9-19
+    if ((n >= 3 && n <= 10) || n == 14 || n == 16) return true; // max_seq_helper.h:9-19
+    return g_extended_n && n >= 11 && n <= 15;                  // 11, 12, 13, 15: one GPU only (no partitioned kernels built)
 }
 
 extern "C" int pg_ctx_create(int n_seq, const char *const *seqs, const int *lens, const int32_t *cost90x90, int gap_open,

@@ -240,6 +240,7 @@ int pg_launch_expand(pg_ctx *ctx, const void *d_parents, int64_t k, int vec_size
     case X:     \
         return launch_expand_n<X>(ctx, d_parents, k, vec_size, d_out, d_counts, st);
         CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(14) CASE(16)
+        CASE(11) CASE(12) CASE(13) CASE(15) // pg_allow_extended_n
 #undef CASE
     default:
         return pg_fail(ctx, PG_ERR_ARG, "unsupported number of sequences (reference supports 3-10, 14, 16: max_seq_helper.h:9-19)");

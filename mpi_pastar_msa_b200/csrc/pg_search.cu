@@ -1996,6 +1996,12 @@ int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st, bool inbox = false)
         CASE(5) CASE(7)
 #else
         CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(14) CASE(16)
+#define CASE1(X) /* pg_allow_extended_n: the one-partition kernel only */ \
+    case X:                                                               \
+        if (mode == 0) return launch_expand_round<X, KEYW, VALW, 0>(ctx, st, inbox); \
+        return pg_fail(ctx, PG_ERR_UNSUPPORTED, "the partitioned search is not built for this number of sequences");
+        CASE1(11) CASE1(12) CASE1(13) CASE1(15)
+#undef CASE1
 #endif
 #undef CASE
     }
@@ -2203,6 +2209,8 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
 {
     if (!ctx || !cfg || cfg->n_parts < 1 || cfg->n_parts > 64 || cfg->part < 0 || cfg->part >= cfg->n_parts) return PG_ERR_ARG;
     if (!ctx->tables_built) return pg_fail(ctx, PG_ERR_STATE, "pg_build_pair_tables has not run");
+    if (cfg->n_parts > 1 && (ctx->n == 11 || ctx->n == 12 || ctx->n == 13 || ctx->n == 15))
+        return pg_fail(ctx, PG_ERR_UNSUPPORTED, "the partitioned search is not built for this number of sequences (pg_allow_extended_n: one GPU only)");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     pg_search_free(ctx);
     SearchState *s = new SearchState();
