@@ -211,6 +211,13 @@ int pg_search_set_peers(pg_ctx *ctx, void *const *peer_inbox, int n);
  * and calls pg_search_insert_inbox_async, whose insert kernels read the counts from device memory.  With nbuf = 2
  * the inboxes (2 x n_parts regions) and count arrays alternate per round, so that one barrier per round is enough. */
 int pg_search_set_peer_counts(pg_ctx *ctx, void *const *peer_counts, int n, int nbuf);
+/* Data-flow synchronisation instead of a barrier (needs nbuf = 2): every count a partition publishes carries the exchange
+ * round, and pg_search_insert_inbox_async starts with a one-block kernel that waits, on the device, until every source's
+ * count of the current round has arrived.  The driver then calls pg_search_round_async / pg_search_insert_inbox_async
+ * back to back with NO cross-GPU barrier in between: a count is written after the data it covers, and no partition can
+ * run more than one round ahead of another (its next round waits for that partition's next count).  A peer that never
+ * delivers ends the wait after ~20 s with PG_ERR_STATE. */
+int pg_search_set_device_sync(pg_ctx *ctx, int enable);
 /* pg_search_round without the host synchronisation (launches only); pair with pg_search_sync. */
 int pg_search_round_async(pg_ctx *ctx, int32_t f_limit);
 int pg_search_insert_inbox_async(pg_ctx *ctx);

@@ -93,6 +93,7 @@ def load_library():
         "pg_search_set_peers": ([vp, C.POINTER(vp), i32], i32),
         "pg_search_set_peer_counts": ([vp, C.POINTER(vp), i32, i32], i32),
         "pg_search_round_async": ([vp, C.c_int32], i32),
+        "pg_search_set_device_sync": ([vp, i32], i32),
         "pg_search_insert_inbox_async": ([vp], i32),
         "pg_search_sync": ([vp], i32),
         "pg_multi_search": ([C.POINTER(vp), i32, C.POINTER(SearchConfig), C.POINTER(Result), C.POINTER(Result), C.POINTER(C.c_char_p)], i32),
@@ -113,7 +114,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_allow_extended_n", "pg_gpu_weights", "pg_bench_int_peak", "pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_search_set_device_sync", "pg_allow_extended_n", "pg_gpu_weights", "pg_bench_int_peak", "pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -408,6 +409,9 @@ class PastarGPU:
     def search_set_peer_counts(self, ptrs, nbuf=2):
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         self._ck(self.L.pg_search_set_peer_counts(self.h, arr, len(ptrs), nbuf))
+
+    def search_set_device_sync(self, enable=True):
+        self._ck(self.L.pg_search_set_device_sync(self.h, 1 if enable else 0))
 
     def search_round_async(self, f_limit=2**31 - 1):
         self._ck(self.L.pg_search_round_async(self.h, f_limit))

@@ -106,6 +106,8 @@ struct SearchState {
     void *peer_inbox[16] = {nullptr};
     unsigned long long *peer_counts[16] = {nullptr}; // P2P mode: every partition's uint64[nbuf][n_parts] "records from source s"
     int p2p_nbuf = 1, p2p_buf = 0;                   // double-buffered inboxes: one cross-GPU barrier per round is enough
+    bool stamped = false;                            // counts carry the exchange round: receivers wait for them on the device, no barrier
+    long long xround = 0;                            // exchange rounds completed
     bool p2p = false;
     bool forward = false;      // P2P parent forwarding (pg_search_config.reserved == 2)
     bool merge_expand = false; // forwarding: own and forwarded parents expanded by ONE launch after the barrier
@@ -804,6 +806,8 @@ __device__ __forceinline__ unsigned successor_owners(const DevProblem &p, const 
     return set & ~(1u << part);
 }
 
+constexpr int STAMP_SHIFT = 40; // counts stay below 2^40; the bits above carry the exchange round + 1 (data-flow synchronisation)
+constexpr unsigned long long COUNT_MASK = (1ull << STAMP_SHIFT) - 1ull;
 constexpr uint32_t PROBE_MISS = 0xffffffffu;        // stash: the probe found no block of its own at the home directory slot
 constexpr unsigned long long HINT_FLAG = 1ull << 31; // record word KEYW+1: {start slot : 32 | HINT_FLAG | move mask : 16}
 constexpr int RING_CAP = 64;                         // survivor ring, items per warp
@@ -1007,7 +1011,7 @@ __device__ __noinline__ unsigned long long outbox_reserve(const DevSearch &d, un
 // Append `count` (<= 32) ring items, contiguous from ring index `from`, to the round's survivor list: one atomic,
 // coalesced 8-byte stores.
 template <int XW>
-__device__ __forceinline__ void ring_flush(const DevSearch &d, const unsigned long long *wq, unsigned from, unsigned count, int lane)
+__device__ __noinline__ void ring_flush(const DevSearch &d, const unsigned long long *wq, unsigned from, unsigned count, int lane)
 {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&d.ctrl->surv_n, (unsigned long long)count);
@@ -1060,7 +1064,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     __shared__ int s_skip;
     if (threadIdx.x == 0) {
         unsigned long long any = 0;
-        for (int rg = 0; rg < ps.n; rg++) any |= *ps.count[rg];
+        for (int rg = 0; rg < ps.n; rg++) any |= *ps.count[rg] & COUNT_MASK;
         s_skip = (c->done || c->error || any == 0) ? 1 : 0;
     }
     __syncthreads();
@@ -1167,7 +1171,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     const int stride = gridDim.x * GROUPS;
     for (int rg = 0; rg < ps.n; rg++) {
     const unsigned long long *live = ps.base[rg];
-    const int live_n = (int)min(*ps.count[rg], ps.cap);
+    const int live_n = (int)min(*ps.count[rg] & COUNT_MASK, ps.cap);
     int pi = blockIdx.x * GROUPS + grp;
     unsigned long long nk0 = 0, nk1 = 0, nval = 0;
     if (pi < live_n) {
@@ -1499,7 +1503,7 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
         int skip = (threadIdx.x & 31) == 0 ? c->error : 0;
         if (__shfl_sync(0xffffffffu, skip, 0)) return;
     }
-    const long long n = (long long)min(*n_ptr, n_max);
+    const long long n = (long long)min(*n_ptr & COUNT_MASK, n_max);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->table_used, (unsigned long long)n); // records seen by insert kernels
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     int min_b = INT_MAX;
@@ -1686,10 +1690,30 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 }
 
 // P2P mode: tell every owner how many records this partition stored into its inbox this round.
-__global__ void publish_counts_kernel(const __grid_constant__ DevSearch d)
+__global__ void publish_counts_kernel(const __grid_constant__ DevSearch d, unsigned long long stamp)
 {
     const int dst = threadIdx.x;
-    if (dst < d.n_parts && d.peer_counts[dst]) d.peer_counts[dst][d.part] = d.outbox_count[dst];
+    if (dst < d.n_parts && d.peer_counts[dst]) {
+        __threadfence_system(); // the records / parents this count covers were stored by earlier kernels of this stream
+        d.peer_counts[dst][d.part] = (stamp << STAMP_SHIFT) | d.outbox_count[dst];
+    }
+}
+// Device-side wait for the other partitions' counts of this exchange round (replaces a cross-GPU barrier: a count is
+// written after the data it covers, and a partition cannot run more than one round ahead because its next round waits
+// for this partition's next stamp).  One thread per source; gives up after ~20 s (a peer failed) with an error.
+__global__ void wait_counts_kernel(const __grid_constant__ DevSearch d, unsigned long long stamp)
+{
+    const int src = threadIdx.x;
+    if (src >= d.n_parts || src == d.part) return;
+    const volatile unsigned long long *slot = d.peer_counts[d.part] + src;
+    const long long t0 = clock64();
+    while ((*slot >> STAMP_SHIFT) < stamp) {
+        if (clock64() - t0 > 40000000000ll) {
+            d.ctrl->error = 6;
+            break;
+        }
+    }
+    __threadfence_system();
 }
 
 
@@ -2097,7 +2121,7 @@ int launch_round(pg_ctx *ctx, int f_limit)
             else
                 forward_kernel<2><<<(unsigned)fgrid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
             PG_CUDA(ctx, cudaGetLastError());
-            publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(d);
+            publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(d, s->stamped ? (unsigned long long)(s->xround + 1) : 0ull);
             PG_CUDA(ctx, cudaGetLastError());
         }
     }
@@ -2112,7 +2136,7 @@ int launch_round(pg_ctx *ctx, int f_limit)
     }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     if (!s->forward && s->p2p && s->peer_counts[0]) {
-        publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx));
+        publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx), s->stamped ? (unsigned long long)(s->xround + 1) : 0ull);
         PG_CUDA(ctx, cudaGetLastError());
     }
     s->rounds++;
@@ -2139,6 +2163,8 @@ int sync_ctrl(pg_ctx *ctx)
         return pg_fail(ctx, PG_ERR_CAPACITY, "f exceeded the bucket range");
     case 5:
         return pg_fail(ctx, PG_ERR_UNSUPPORTED, "a successor's f fell below h(start): the heuristic is not consistent for this cost model");
+    case 6:
+        return pg_fail(ctx, PG_ERR_STATE, "a peer partition did not deliver its counts for this round (device-side wait timed out)");
     default:
         return pg_fail(ctx, PG_ERR_CAPACITY, "outbox overflow: lower batch_target");
     }
@@ -2444,6 +2470,16 @@ extern "C" int pg_search_set_peer_counts(pg_ctx *ctx, void *const *peer_counts, 
     return PG_OK;
 }
 
+extern "C" int pg_search_set_device_sync(pg_ctx *ctx, int enable)
+{
+    if (!ctx || !ctx->search) return PG_ERR_ARG;
+    SearchState *s = ctx->search;
+    if (enable && (s->p2p_nbuf != 2 || !s->peer_counts[s->cfg.part]))
+        return pg_fail(ctx, PG_ERR_STATE, "pg_search_set_device_sync needs pg_search_set_peer_counts with two buffers");
+    s->stamped = enable != 0;
+    return PG_OK;
+}
+
 extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
 {
     if (!ctx || !ctx->search) return PG_ERR_ARG;
@@ -2451,6 +2487,10 @@ extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
     if (!s->p2p || !s->peer_counts[s->cfg.part]) return pg_fail(ctx, PG_ERR_STATE, "pg_search_insert_inbox_async needs pg_search_set_peers and pg_search_set_peer_counts");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
+    if (s->stamped) { // data-flow synchronisation: wait on the device for every source's count of this exchange round
+        wait_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx), (unsigned long long)(s->xround + 1));
+        PG_CUDA(ctx, cudaGetLastError());
+    }
     if (s->profile && (rc = prof_event2(ctx)) != PG_OK) return rc;
     if (s->forward) {
         // expand the parents the other partitions forwarded (only the successors this partition owns), then insert
@@ -2468,6 +2508,7 @@ extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
     }
     if (s->profile && (rc = prof_event2(ctx)) != PG_OK) return rc;
     s->p2p_buf = (s->p2p_buf + 1) % s->p2p_nbuf;
+    s->xround++;
     return PG_OK;
 }
 

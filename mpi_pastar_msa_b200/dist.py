@@ -15,6 +15,8 @@ ranks of best_goal_g`.
 The engine is the CUDA context (PastarGPU).  The driver only moves bytes; torch.distributed is plumbing (NCCL on GPUs,
 gloo in the CPU tests where a test-only engine stands in for the kernels).
 """
+import os
+
 import numpy as np
 
 INT_MAX = 2**31 - 1
@@ -97,6 +99,11 @@ class CudaEngineP2P(CudaEngine):
         self.hdl_c = symm.rendezvous(self.counts, dist.group.WORLD)
         gpu.search_set_peers([int(self.hdl.buffer_ptrs[r]) for r in range(n_parts)])
         gpu.search_set_peer_counts([int(self.hdl_c.buffer_ptrs[r]) for r in range(n_parts)], 2)
+        # data-flow synchronisation (default): the counts carry the round and the receiver waits for them on the device, so
+        # there is no barrier kernel between a round's two halves; PG_DEVICE_SYNC=0 goes back to one signal-pad barrier
+        self.device_sync = os.environ.get("PG_DEVICE_SYNC", "1") != "0"
+        if self.device_sync:
+            gpu.search_set_device_sync(True)
         self.sent = self._wrap64(gpu.search_outbox_counts_dev(), n_parts)   # this round's records per destination
         self.sent_total = torch.zeros(1, dtype=torch.int64, device=self.device)
         torch.cuda.synchronize()
@@ -114,8 +121,9 @@ class CudaEngineP2P(CudaEngine):
     def round_and_exchange(self, f_limit, dist):
         self.g.search_round_async(f_limit)     # remote successors + their counts are on their way to the owners
         self.sent_total += self.sent.sum()     # bookkeeping only (device side)
-        self.hdl.barrier(channel=0)            # every partition's stores of this round are complete and visible
-        self.g.search_insert_inbox_async()     # dedupe + push what the other partitions sent; flips the buffers
+        if not self.device_sync:
+            self.hdl.barrier(channel=0)        # every partition's stores of this round are complete and visible
+        self.g.search_insert_inbox_async()     # (device sync: waits for the sources' counts first) dedupe + push; flips the buffers
 
     def status(self):
         self.g.search_sync()

@@ -87,7 +87,7 @@ def test_partitioned_kinase_two_parts(gpu_lib):
     assert r["g"] == 421546
 
 
-def p2p_search(m, seqs, parts, batch, hash_type, shift, mode, cap=1 << 22):
+def p2p_search(m, seqs, parts, batch, hash_type, shift, mode, cap=1 << 22, device_sync=False):
     """The device-driven P2P rounds (pg_search_round_async / pg_search_insert_inbox_async) with G logical partitions on
     ONE GPU: every partition's inbox and count array are plain device buffers of this process, so "peer-mapped" is
     simply their address, and the cross-GPU barrier is a device synchronise.  mode 1 = successor records stored by the
@@ -106,6 +106,8 @@ def p2p_search(m, seqs, parts, batch, hash_type, shift, mode, cap=1 << 22):
     for G in Gs:
         G.search_set_peers([t.data_ptr() for t in inbox])
         G.search_set_peer_counts([t.data_ptr() for t in counts], 2)
+        if device_sync:  # stamped counts + device-side wait instead of a barrier between the two halves of a round
+            G.search_set_device_sync(True)
     best, rounds = INT_MAX, 0
     while True:
         for _ in range(3):  # a few rounds between status checks, as the torchrun driver does
@@ -242,3 +244,16 @@ def test_multi_search_wide_n_one_device(gpu_lib, name):
     assert tot["finished"] == 1 and tot["g"] == ref, tot
     for G in Gs:
         G.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name,parts,batch,ht,sh", [("PF08184", 2, 64, "FZORDER", 3), ("fam5x60", 3, 64, "FZORDER", 0), ("fam8x20", 4, 4096, "PZORDER", 1),
+                                                    ("fam4x150", 8, 4096, "FZORDER", 12), ("kinase", 2, 16384, "PZORDER", 6)])
+def test_p2p_modes_device_sync(gpu_lib, name, parts, batch, ht, sh, mode):
+    """Data-flow synchronisation (pg_search_set_device_sync): counts carry the exchange round and the receiving half of a
+    round waits for them on the device.  Same optimal costs; on one device every publish precedes every wait in stream
+    order, the cross-device ordering is exercised by bench.py --gpus N's parity gate."""
+    seqs = CASES[name]
+    ref = KNOWN_OPT.get(name) or O.Problem(seqs).astar(want_rows=False)["g"]
+    r = p2p_search(gpu_lib, seqs, parts, batch, ht, sh, mode, cap=1 << 24, device_sync=True)
+    assert r["g"] == ref, (name, parts, mode, r)
