@@ -83,7 +83,7 @@ struct pg_ctx {
     // resident CTAs per SM of the kernels that opt in to > 48 KB of dynamic shared memory; 0 = attribute not set yet on
     // this context's device (N and the key width are fixed per context, so one slot per kernel / mode is enough)
     int occ_expand_batch = 0;
-    int occ_expand_probe[3] = {0, 0, 0};
+    int occ_expand_probe[4] = {0, 0, 0, 0}; // per mode; [3] = mode 2 without per-successor owner arithmetic
     std::string err;
 };
 

@@ -1030,7 +1030,9 @@ __device__ __noinline__ void ring_flush(const DevSearch &d, const unsigned long 
 #ifndef PG_EXPAND_CTAS
 #define PG_EXPAND_CTAS 3 // resident CTAs per SM the expand kernel is compiled for (register budget 65536 / 256 / this)
 #endif
-template <int N, int KEYW, int VALW, int MODE>
+// LOOPOWN = false: the owner hash reads only coordinates that are lane bits (PZORDER, PSUM, FZORDER with its bits in the
+// first A coordinates), so a lane's successors all have one owner and the per-successor owner arithmetic is not compiled.
+template <int N, int KEYW, int VALW, int MODE, bool LOOPOWN = true>
 __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ DevSearch d,
                                                               const __grid_constant__ OwnerArgs oa, const __grid_constant__ ParentSrc ps)
 {
@@ -1231,10 +1233,12 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     w1 |= (((pc + 1u) >> oa.bit[m]) & 1u) << m;
                 }
                 wbase = (w0 & ~lanemask) | (w1 & lanemask);
+                if constexpr (LOOPOWN) {
 #pragma unroll
-                for (int b = 0; b < C::HB; b++) {
-                    wflip[b] = (w0 ^ w1) & hmask[b];
-                    wany |= wflip[b];
+                    for (int b = 0; b < C::HB; b++) {
+                        wflip[b] = (w0 ^ w1) & hmask[b];
+                        wany |= wflip[b];
+                    }
                 }
                 uniform = wany == 0; // most parents lie inside one partition's cell in every loop coordinate
             } else {
@@ -1245,7 +1249,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                 qmod = (int)((psum >> oa.shift) % (unsigned)d.n_parts);
                 rk = (int)(psum & ((1u << oa.shift) - 1u)) + ksub;
                 const int kmax = sum_nd > C::A ? sum_nd - C::A : 0; // loop bits that count towards the sum
-                uniform = ((unsigned)rk >> oa.shift) == ((unsigned)(rk + kmax) >> oa.shift);
+                uniform = !LOOPOWN || ((unsigned)rk >> oa.shift) == ((unsigned)(rk + kmax) >> oa.shift);
                 wbase = (unsigned)qmod + ((unsigned)rk >> oa.shift); // < 64 + 17: s_mod reduces it
             }
         }
@@ -1319,7 +1323,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     int own = d.part;
                     if constexpr (MODE == 2) v = v && !own_none;
                     if constexpr (MULTI) {
-                        if (v && !own_all && !lane_foreign) {
+                        if (LOOPOWN && v && !own_all && !lane_foreign) {
                             if (!zorder) {
                                 // the successor's sum is the parent's plus the sequences moved: (sum >> shift) % n_parts
                                 const int kh = sum_nd > C::A ? __popc((unsigned)high & ((1u << (sum_nd - C::A)) - 1u)) : 0;
@@ -1958,7 +1962,7 @@ OwnerArgs owner_args(const pg_ctx *ctx)
 
 // MODE as in expand_probe_kernel; inbox = false: this partition's own live parents, true: the parents forwarded by the
 // other partitions (MODE 2)
-template <int N, int KEYW, int VALW, int MODE>
+template <int N, int KEYW, int VALW, int MODE, bool LOOPOWN = true>
 int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
 {
     using C = ExpCfg<N>;
@@ -1971,10 +1975,10 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
     const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H + 8 * 8 * RING_CAP * XW +
                         sizeof(int) * (size_t)GROUPS * C::GROUP_INTS + (size_t)PF * 256 * (VALW + 12);
     // per-device state (cudaFuncSetAttribute applies to the current device only): cached per context and kernel mode
-    int &occ = ctx->occ_expand_probe[MODE];
+    int &occ = ctx->occ_expand_probe[MODE == 2 && !LOOPOWN ? 3 : MODE];
     if (!occ) {
-        PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, VALW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, VALW, MODE>, 256, smem));
+        PG_CUDA(ctx, cudaFuncSetAttribute(expand_probe_kernel<N, KEYW, VALW, MODE, LOOPOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_probe_kernel<N, KEYW, VALW, MODE, LOOPOWN>, 256, smem));
         if (occ < 1) occ = 1;
     }
     // persistent grid: resident CTAs per SM x SM count, capped by the parent groups of a full batch
@@ -2000,9 +2004,22 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
             ps.n++;
         }
     }
-    expand_probe_kernel<N, KEYW, VALW, MODE><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, d, owner_args(ctx), ps);
+    expand_probe_kernel<N, KEYW, VALW, MODE, LOOPOWN><<<(unsigned)grid, 256, smem, st>>>(ctx->dp, d, owner_args(ctx), ps);
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
+}
+
+// does the owner hash read a coordinate that the expand kernel enumerates in its per-lane loop (coordinates >= A)?
+template <int N>
+bool loop_owner(const pg_ctx *ctx)
+{
+    using C = ExpCfg<N>;
+    const OwnerArgs oa = owner_args(ctx);
+    if (oa.type == PG_HASH_PSUM) return false;         // coordinates 0 and 1: lane bits for every N >= 3
+    if (oa.type == PG_HASH_FSUM) return N > C::A;
+    for (int m = 0; m < oa.nb; m++)
+        if (oa.co[m] >= C::A) return true;
+    return false;
 }
 
 template <int KEYW, int VALW>
@@ -2015,6 +2032,7 @@ int launch_expand_round_k(pg_ctx *ctx, cudaStream_t st, bool inbox = false)
     case X:                                                                        \
         if (mode == 0) return launch_expand_round<X, KEYW, VALW, 0>(ctx, st, inbox);     \
         if (mode == 1) return launch_expand_round<X, KEYW, VALW, 1>(ctx, st, inbox);     \
+        if (!loop_owner<X>(ctx)) return launch_expand_round<X, KEYW, VALW, 2, false>(ctx, st, inbox); \
         return launch_expand_round<X, KEYW, VALW, 2>(ctx, st, inbox);
 #ifdef PG_DEV_BUILD // experiment builds (PG_VARIANT=...): only the sizes the measurements use, a third of the compile time
         CASE(5) CASE(7)
@@ -2247,7 +2265,7 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     s->xrec = pg_xrec_stride(ctx);
     s->D = std::min(ctx->n, 7);
     s->DL = ctx->dp.key_bits >= 2 ? std::min(ctx->n, s->keyw == 1 ? 4 : 3) : 0;
-    ctx->occ_expand_probe[0] = ctx->occ_expand_probe[1] = ctx->occ_expand_probe[2] = 0; // the value width may differ from the last search's
+    ctx->occ_expand_probe[0] = ctx->occ_expand_probe[1] = ctx->occ_expand_probe[2] = ctx->occ_expand_probe[3] = 0; // the value width may differ from the last search's
 
     s->batch_target = cfg->batch_target > 0 ? cfg->batch_target : 16384;
 
