@@ -124,6 +124,11 @@ struct SearchState {
     double kernel_ms = 0;
     int64_t rounds = 0;
     bool active = false;
+    // pg_search_rounds: a group of rounds captured once as a CUDA graph (every round is the same launches with the same
+    // arguments; all per-round state lives in the device control block) and replayed
+    cudaGraphExec_t rounds_exec = nullptr;
+    int rounds_group = 0, rounds_flimit = 0;
+    cudaStream_t rounds_stream = nullptr;
 };
 
 namespace {
@@ -2235,6 +2240,7 @@ void pg_search_free(pg_ctx *ctx)
     cudaFree(s->d_host_counts);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     if (s->h_outbox_count) cudaFreeHost(s->h_outbox_count);
+    if (s->rounds_exec) cudaGraphExecDestroy(s->rounds_exec);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
@@ -2453,7 +2459,39 @@ extern "C" int pg_search_rounds(pg_ctx *ctx, int32_t rounds, int32_t f_limit)
     if (!ctx || !ctx->search || !ctx->search->active) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
     if (ctx->search->cfg.n_parts != 1) return pg_fail(ctx, PG_ERR_ARG, "pg_search_rounds is for a single partition");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int r = 0; r < rounds; r++) {
+    SearchState *s = ctx->search;
+    int r = 0;
+    constexpr int GROUP = 8;
+    if (!s->profile && rounds >= GROUP && !getenv("PG_NO_GRAPH")) {
+        if (s->rounds_exec && (s->rounds_flimit != f_limit || s->rounds_stream != ctx->stream)) {
+            cudaGraphExecDestroy(s->rounds_exec);
+            s->rounds_exec = nullptr;
+        }
+        if (!s->rounds_exec && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            cudaGraph_t graph = nullptr;
+            int rc = PG_OK;
+            for (int k = 0; k < GROUP && rc == PG_OK; k++) rc = launch_round(ctx, f_limit);
+            s->rounds -= GROUP; // captured, not run
+            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc == PG_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&s->rounds_exec, graph, 0) == cudaSuccess) {
+                s->rounds_group = GROUP;
+                s->rounds_flimit = f_limit;
+                s->rounds_stream = ctx->stream;
+            } else {
+                cudaGetLastError();
+                s->rounds_exec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != PG_OK) return rc;
+        } else if (!s->rounds_exec) {
+            cudaGetLastError();
+        }
+        for (; s->rounds_exec && r + s->rounds_group <= rounds; r += s->rounds_group) {
+            PG_CUDA(ctx, cudaGraphLaunch(s->rounds_exec, ctx->stream));
+            s->rounds += s->rounds_group;
+        }
+    }
+    for (; r < rounds; r++) {
         int rc = launch_round(ctx, f_limit);
         if (rc != PG_OK) return rc;
     }
