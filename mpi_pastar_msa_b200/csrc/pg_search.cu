@@ -1496,7 +1496,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
 // from device memory, so a driver can chain rounds without a host round trip.  Every step of the chain
 //     record -> directory word (-> claim a free slot for a new block) -> value -> CAS value (strictly better g)
 //            -> bucket atomicAdd -> pool store
-// is issued for 4 records per thread before any of its results is used, so 4 dependent chains overlap per thread.
+// is issued for 2 records per thread before any of its results is used, so 2 dependent chains overlap per thread.
 // What does not fit the straight line (directory collision, a CAS lost to a concurrent writer, a bucket whose chunk is
 // full) takes the one-record-at-a-time path (upsert_from / bucket_place_slow).
 template <int KEYW, int VALW>
@@ -1505,7 +1505,9 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 {
     typedef typename ValT<VALW>::T T;
     constexpr int XW = KEYW == 1 ? 3 : 4;
-    constexpr int PF = 4;
+    constexpr int PF = 2; // records in flight per thread.  The kernel sits at the rate of random HBM transactions (one cold value line per record):
+                          // 2 / 4 / 8 in flight measured 162 / 175 / 260 us, a three-stage software pipeline (loads of two batches in flight while a
+                          // third does its atomics) 159 us - profiles/r02_experiments.md
     enum { DONE = 0, DIR = 1, VAL = 2, PUSH = 3, WALK = 4 };
     SearchCtrl *c = d.ctrl;
     {   // warp-uniform early exit: other CTAs of this launch may raise c->error, and warp-level ballots follow
