@@ -822,7 +822,11 @@ template <int KEYW, int VALW>
 __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevSearch d)
 {
     typedef typename ValT<VALW>::T T;
-    constexpr int PF = 4; // pops per thread, each step of their dependent chains (plan -> pool -> table) issued for all four
+#ifndef PG_CLAIM_PF
+#define PG_CLAIM_PF 1 // 4 / 2 / 1 pops per thread: 58 / 51 / 48 us - with one pop per thread the batch is 3.5 waves of CTAs whose
+                      // phases (pool read, value line, atomic) overlap instead of every thread of one wave marching through them in step
+#endif
+    constexpr int PF = PG_CLAIM_PF; // pops per thread, each step of their dependent chains (plan -> pool -> table) issued for all of them
     __shared__ uint32_t s_plan[PLAN_SM];
     __shared__ int s_wtot[8];
     __shared__ unsigned long long s_base;
@@ -872,9 +876,15 @@ __global__ void __launch_bounds__(256) claim_kernel(const __grid_constant__ DevS
         for (int j = 0; j < PF; j++) {
             old[j] = (T)1 << d.nb; // "already closed": not live
             klo[j] = khi[j] = 0;
-            if (bi[j] < batch_n) {
-                // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion.  The block's key
-                // never changes once the block exists, so it is read alongside.
+            // Three of four popped entries are stale (the node was closed through a better entry): a plain load of the
+            // value decides those - ONE random line, where the atomic plus the block's key cost two and a write-back.
+            if (bi[j] < batch_n) old[j] = ld_val<VALW>(val_ptr<VALW>(d, slot[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            if (!val_closed<VALW>(d, old[j])) {
+                // mark closed: set the (inverted) open bit; whoever sees it clear owns the expansion (PAStar.cpp:344-351).
+                // The block's key never changes once the block exists, so it is read alongside.
                 old[j] = atomicOr(val_ptr<VALW>(d, slot[j]), (T)1 << d.nb);
                 const unsigned long long *e = d.dir + (size_t)(slot[j] >> d.D) * KEYW;
                 klo[j] = ld_cg_u64(e);
@@ -1187,6 +1197,8 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
         if constexpr (KEYW == 2) nk1 = __ldg(r + ps.cap);
         nval = __ldg(r + KEYW * ps.cap);
     }
+    // (a dynamic deal of the parents - GPW at a time from a counter, the next deal's atomic in flight during the expansion -
+    // measured the same 381 us as this static round-robin: the groups' 13-or-14-parents tail is not what the launch waits for)
     for (int wfirst = blockIdx.x * GROUPS + warp * GPW; wfirst < live_n; wfirst += stride, pi += stride) {
         bool act = pi < live_n;
         Key<KEYW> pkey = Key<KEYW>::zero();
@@ -1496,17 +1508,23 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
 // from device memory, so a driver can chain rounds without a host round trip.  Every step of the chain
 //     record -> directory word (-> claim a free slot for a new block) -> value -> CAS value (strictly better g)
 //            -> bucket atomicAdd -> pool store
-// is issued for 2 records per thread before any of its results is used, so 2 dependent chains overlap per thread.
+// runs for one record per thread at a time (PG_INS_PF): the warps of the 8 resident CTAs per SM drift apart, so their phases overlap.
 // What does not fit the straight line (directory collision, a CAS lost to a concurrent writer, a bucket whose chunk is
 // full) takes the one-record-at-a-time path (upsert_from / bucket_place_slow).
+#ifndef PG_INS_CTAS
+#define PG_INS_CTAS 4
+#endif
 template <int KEYW, int VALW>
-__global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
+__global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
                                                         const unsigned long long *__restrict__ n_ptr, unsigned long long n_max)
 {
     typedef typename ValT<VALW>::T T;
     constexpr int XW = KEYW == 1 ? 3 : 4;
-    constexpr int PF = 2; // records in flight per thread.  The kernel sits at the rate of random HBM transactions (one cold value line per record):
-                          // 2 / 4 / 8 in flight measured 162 / 175 / 260 us, a three-stage software pipeline (loads of two batches in flight while a
+#ifndef PG_INS_PF
+#define PG_INS_PF 1
+#endif
+    constexpr int PF = PG_INS_PF; // records in flight per thread.  The kernel sits at the rate of random HBM transactions (one cold value line per record):
+                          // 1 / 2 / 4 / 8 in flight measured 158 / 162 / 175 / 260 us, a three-stage software pipeline (loads of two batches in flight while a
                           // third does its atomics) 159 us - profiles/r02_experiments.md
     enum { DONE = 0, DIR = 1, VAL = 2, PUSH = 3, WALK = 4 };
     SearchCtrl *c = d.ctrl;
@@ -2109,7 +2127,7 @@ int launch_insert(pg_ctx *ctx, const void *recs, const unsigned long long *n_ptr
 {
     SearchState *s = ctx->search;
     if (n_max == 0) return PG_OK;
-    const long long grid = std::min<long long>((long long)((n_max + 1023) / 1024), (long long)ctx->sm_count * 8);
+    const long long grid = std::min<long long>((long long)((n_max + 1023) / 1024), (long long)ctx->sm_count * 2 * PG_INS_CTAS);
     PG_DISPATCH_KV(s, (insert_kernel<KW, VW><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max)));
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
@@ -2134,7 +2152,7 @@ int launch_round(pg_ctx *ctx, int f_limit)
     PG_CUDA(ctx, cudaGetLastError());
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     {
-        const long long grid = std::min<long long>((s->batch_target + 1023) / 1024, (long long)ctx->sm_count * 8); // claim: 4 pops per thread
+        const long long grid = std::min<long long>((s->batch_target + 256 * PG_CLAIM_PF - 1) / (256 * PG_CLAIM_PF), (long long)ctx->sm_count * 32); // claim: PG_CLAIM_PF pops per thread
         const long long fgrid = std::min<long long>((s->batch_target + 255) / 256, (long long)ctx->sm_count * 8);
         const DevSearch d = dev_search(ctx);
         PG_DISPATCH_KV(s, (claim_kernel<KW, VW><<<(unsigned)grid, 256, 0, ctx->stream>>>(d)));
