@@ -114,6 +114,11 @@ struct SearchState {
     size_t region_bytes = 0;   // bytes one source may write into one inbox (per buffer)
     int xrec = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // forwarding mode: the survivors of a partition's own parents are inserted on a second stream while the main stream waits
+    // for the other partitions' parents and expands them (insert is bound by HBM transactions, expand by instruction issue)
+    cudaStream_t ins_stream = nullptr;
+    cudaEvent_t ev_split = nullptr, ev_ins = nullptr;
+    bool overlap_insert = false;
     // optional per-launch timing: event triples (before select, between, after expand), harvested at every sync
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -1516,7 +1521,8 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
 #endif
 template <int KEYW, int VALW>
 __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
-                                                        const unsigned long long *__restrict__ n_ptr, unsigned long long n_max)
+                                                        const unsigned long long *__restrict__ n_ptr, unsigned long long n_max,
+                                                        const unsigned long long *__restrict__ begin_ptr)
 {
     typedef typename ValT<VALW>::T T;
     constexpr int XW = KEYW == 1 ? 3 : 4;
@@ -1533,7 +1539,8 @@ __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_c
         if (__shfl_sync(0xffffffffu, skip, 0)) return;
     }
     const long long n = (long long)min(*n_ptr & COUNT_MASK, n_max);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->table_used, (unsigned long long)n); // records seen by insert kernels
+    const long long begin = begin_ptr ? (long long)min(*begin_ptr, (unsigned long long)n) : 0; // records before `begin` were inserted by an earlier launch
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->table_used, (unsigned long long)(n - begin)); // records seen by insert kernels
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     int min_b = INT_MAX;
     const int prune = c->prune_limit;
@@ -1556,7 +1563,7 @@ __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_c
     };
     const long long stride = (long long)gridDim.x * blockDim.x;
     // the trip count is warp-uniform: the deferred ring is a warp-level structure
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * PF) {
+    for (long long i0 = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * PF) {
         Key<KEYW> key[PF], bkey[PF];
         unsigned long long gf[PF], h0[PF], h1[KEYW == 2 ? PF : 1];
         T lv[PF], lo[PF];
@@ -1717,6 +1724,9 @@ __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_c
         if (v[2]) atomicAdd(&c->reopen, (unsigned long long)v[2]);
     }
 }
+
+// Forwarding mode: the survivors appended so far are those of this partition's own parents.
+__global__ void mark_split_kernel(SearchCtrl *c) { c->surv_split = c->surv_n; }
 
 // P2P mode: tell every owner how many records this partition stored into its inbox this round.
 __global__ void publish_counts_kernel(const __grid_constant__ DevSearch d, unsigned long long stamp)
@@ -2123,12 +2133,14 @@ int prof_event2(pg_ctx *ctx)
 }
 
 // records at `recs`, their count in device memory at n_ptr (at most n_max)
-int launch_insert(pg_ctx *ctx, const void *recs, const unsigned long long *n_ptr, unsigned long long n_max)
+int launch_insert(pg_ctx *ctx, const void *recs, const unsigned long long *n_ptr, unsigned long long n_max, const unsigned long long *begin_ptr = nullptr,
+                  cudaStream_t st = nullptr)
 {
     SearchState *s = ctx->search;
     if (n_max == 0) return PG_OK;
+    if (!st) st = ctx->stream;
     const long long grid = std::min<long long>((long long)((n_max + 1023) / 1024), (long long)ctx->sm_count * 2 * PG_INS_CTAS);
-    PG_DISPATCH_KV(s, (insert_kernel<KW, VW><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max)));
+    PG_DISPATCH_KV(s, (insert_kernel<KW, VW><<<(unsigned)grid, 256, 0, st>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max, begin_ptr)));
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
 }
@@ -2176,6 +2188,15 @@ int launch_round(pg_ctx *ctx, int f_limit)
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     if (!s->forward) { // forwarding: the survivors are inserted after the forwarded parents have been expanded as well
         if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
+    } else if (s->overlap_insert) {
+        // ... except those of this partition's own parents: their insert (bound by HBM transactions) runs on a second stream
+        // while this one waits for the other partitions' parents and expands them (bound by instruction issue)
+        mark_split_kernel<<<1, 1, 0, ctx->stream>>>(s->d_ctrl);
+        PG_CUDA(ctx, cudaGetLastError());
+        PG_CUDA(ctx, cudaEventRecord(s->ev_split, ctx->stream));
+        PG_CUDA(ctx, cudaStreamWaitEvent(s->ins_stream, s->ev_split, 0));
+        if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_split, s->surv_cap, nullptr, s->ins_stream)) != PG_OK) return rc;
+        PG_CUDA(ctx, cudaEventRecord(s->ev_ins, s->ins_stream));
     }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     if (!s->forward && s->p2p && s->peer_counts[0]) {
@@ -2242,6 +2263,7 @@ void pg_search_free(pg_ctx *ctx)
 {
     SearchState *s = ctx->search;
     if (!s) return;
+    if (s->ins_stream) cudaStreamSynchronize(s->ins_stream);
     cudaFree(s->d_dir);
     cudaFree(s->d_vals);
     cudaFree(s->d_buckets);
@@ -2261,6 +2283,9 @@ void pg_search_free(pg_ctx *ctx)
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     if (s->h_outbox_count) cudaFreeHost(s->h_outbox_count);
     if (s->rounds_exec) cudaGraphExecDestroy(s->rounds_exec);
+    if (s->ins_stream) cudaStreamDestroy(s->ins_stream);
+    if (s->ev_split) cudaEventDestroy(s->ev_split);
+    if (s->ev_ins) cudaEventDestroy(s->ev_ins);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
@@ -2390,6 +2415,9 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
         PG_CUDA(ctx, cudaMalloc(&s->d_trace, std::max<size_t>(1u << 16, (total + 64) * 4)));
     }
     PG_CUDA(ctx, cudaEventCreate(&s->ev0));
+    PG_CUDA(ctx, cudaStreamCreateWithFlags(&s->ins_stream, cudaStreamNonBlocking));
+    PG_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_split, cudaEventDisableTiming));
+    PG_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_ins, cudaEventDisableTiming));
     PG_CUDA(ctx, cudaEventCreate(&s->ev1));
     {
         // live parents: at most one per popped entry; survivors: at most every successor of every live parent
@@ -2403,6 +2431,7 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     if (cfg->n_parts > 1) {
         s->forward = cfg->reserved == 2;
         s->merge_expand = s->forward && getenv("PG_MERGE_EXPAND") && atoi(getenv("PG_MERGE_EXPAND")) != 0;
+        s->overlap_insert = s->forward && !s->merge_expand && !(getenv("PG_OVERLAP_INSERT") && atoi(getenv("PG_OVERLAP_INSERT")) == 0);
         if (s->forward) {
             // parent forwarding: a destination receives at most every live parent of the round
             s->outbox_cap = (uint64_t)s->batch_target + UNIT;
@@ -2573,7 +2602,12 @@ extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
         // the round's survivors: those of its own parents and of the forwarded ones
         PG_DISPATCH_KV(s, (rc = launch_expand_round_k<KW, VW>(ctx, ctx->stream, true)));
         if (rc != PG_OK) return rc;
-        if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
+        if (s->overlap_insert) { // the own parents' survivors went in on the second stream: only the forwarded parents' are left
+            PG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_ins, 0));
+            if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap, &s->d_ctrl->surv_split)) != PG_OK) return rc;
+        } else if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) {
+            return rc;
+        }
     } else {
         const DevSearch d = dev_search(ctx);
         for (int src = 0; src < s->cfg.n_parts; src++) {

@@ -22,6 +22,19 @@ import numpy as np
 INT_MAX = 2**31 - 1
 
 
+_SYMM_CACHE = {}
+
+
+def _symm_buffer(symm, torch, dist, numel, dtype, device):
+    """A symmetric-memory tensor + its rendezvous handle, cached per (shape, dtype, device, world).  Every rank creates
+    its engines in the same order, so all ranks hit or miss together (the rendezvous is a collective)."""
+    key = (int(numel), str(dtype), device.index, dist.get_world_size())
+    if key not in _SYMM_CACHE:
+        t = symm.empty(int(numel), dtype=dtype, device=device)
+        _SYMM_CACHE[key] = (t, symm.rendezvous(t, dist.group.WORLD))
+    return _SYMM_CACHE[key]
+
+
 class CudaEngine:
     """Adapter: PastarGPU step-wise search -> the byte-tensor interface the driver speaks."""
 
@@ -92,11 +105,11 @@ class CudaEngineP2P(CudaEngine):
         gpu.search_begin(n_parts, part, table_capacity, batch_target, p2p=2 if forward else 1)
         self.xrec = gpu.xrec_stride() if not forward else 8 * (2 if gpu.xrec_stride() == 24 else 3)
         self.region = gpu.search_region_bytes()                        # bytes one source may write into one inbox
-        self.inbox = symm.empty(2 * n_parts * self.region, dtype=torch.uint8, device=self.device)
-        self.hdl = symm.rendezvous(self.inbox, dist.group.WORLD)
-        self.counts = symm.empty(2 * n_parts, dtype=torch.int64, device=self.device)
-        self.counts.zero_()
-        self.hdl_c = symm.rendezvous(self.counts, dist.group.WORLD)
+        # peer-mapped buffers are kept for the life of the process and reused by later searches of the same shape: the
+        # allocation + handle exchange (a collective over the store) costs ~0.4 s, more than a sub-second search
+        self.inbox, self.hdl = _symm_buffer(symm, torch, dist, 2 * n_parts * self.region, torch.uint8, self.device)
+        self.counts, self.hdl_c = _symm_buffer(symm, torch, dist, 2 * n_parts, torch.int64, self.device)
+        self.counts.zero_()  # stamps of an earlier search must not be taken for this one's
         gpu.search_set_peers([int(self.hdl.buffer_ptrs[r]) for r in range(n_parts)])
         gpu.search_set_peer_counts([int(self.hdl_c.buffer_ptrs[r]) for r in range(n_parts)], 2)
         # data-flow synchronisation (default): the counts carry the round and the receiver waits for them on the device, so
