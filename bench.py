@@ -326,8 +326,8 @@ def run_ours(args, rank, world):
                     break
             dr.step(rounds=w_steps)
             _, _, t0_ = dr.step()
-            gpu.search_profile(True)
-            p0 = gpu.search_status()[2]
+            # pass 1, the timed region of `value`: k_steps rounds as the product runs them (device-driven; groups of 8 rounds
+            # replayed as a CUDA graph, dist.CudaEngineP2P.rounds), one status exchange at the end
             smp = ClockSampler(local) if sample_clocks else None
             if smp:
                 smp.start()
@@ -346,10 +346,19 @@ def run_ours(args, rank, world):
                 smp.stop_flag = True
             tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sent1 = dr.bytes_sent
+            # pass 2, rank 0's per-kernel times: the next k_steps rounds with an event pair around every launch (plain launches)
+            gpu.search_profile(True)
+            p0 = gpu.search_status()[2]
+            if ch:
+                dr.step(rounds=k_steps)
+            else:
+                for _ in range(k_steps):
+                    dr.step()
             p1 = gpu.search_status()[2]
             gpu.search_profile(False)
             out = {"max_ms": float(tt.item()), "tot0": t0_, "tot1": t1_, "ramp": rmp, "how": how, "sampler": smp,
-                   "nvlink_bytes_per_step_per_gpu": (dr.bytes_sent - s0) / k_steps,
+                   "nvlink_bytes_per_step_per_gpu": (sent1 - s0) / k_steps,
                    "rank0_kernel_ms_per_step": {k: (p1[k] - p0[k]) / k_steps for k in ("select_ms", "claim_ms", "expand_ms", "insert_ms", "inbox_ms")},
                    "rank0_records_inserted_per_step": (p1["survivors"] - p0["survivors"]) / k_steps,
                    "forward": isinstance(e, CudaEngineP2P) and e.forward, "p2p": isinstance(e, CudaEngineP2P)}

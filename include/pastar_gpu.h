@@ -197,6 +197,11 @@ int pg_search_round(pg_ctx *ctx, int32_t f_limit);
 int pg_search_rounds(pg_ctx *ctx, int32_t rounds, int32_t f_limit);
 /* Per-launch CUDA-event timing of the select and expand kernels (off by default: two event records per launch). */
 int pg_search_profile(pg_ctx *ctx, int enable);
+/* Device-driven P2P rounds (pg_search_round_async + pg_search_insert_inbox_async) take the same arguments every second
+ * round, so a caller may capture an even number of them into a CUDA graph on the context's stream and replay it.  The
+ * library's own round counter (pg_result.rounds / pg_search_status) only sees the calls it executes: `delta` adds the
+ * replayed rounds (or takes back the ones that were captured, not run). */
+int pg_search_note_rounds(pg_ctx *ctx, int64_t delta);
 /* Device pointer + record count of the outbox for partition dst (valid until the next round). */
 int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count);
 /* P2P mode (the fused compute + exchange variant): give every partition's inbox base as seen from THIS device

@@ -53,7 +53,8 @@ struct SearchCtrl {          // lives in device memory; mirrored to pinned host 
     unsigned long long pops, expansions, generated, reopen, inserted, pushed, pruned, table_used; // table_used: records seen by insert kernels
     unsigned long long surv_n;   // local survivors of the current round (records in SearchState::d_surv)
     unsigned long long live_n;   // live parents of the current round (after the closed-bit claim)
-    unsigned long long surv_split; // forwarding mode: survivors of this partition's own parents (they are inserted while the forwarded parents are expanded)
+    unsigned long long xround;   // exchange rounds completed (device-driven P2P modes): the stamp of the counts is xround + 1, kept on
+                                 // the device so that a round's launches take the same arguments every time (CUDA-graph replay)
     int free_top[16];            // open-list pool: chunks on the free stack of every size class (log2 units)
     unsigned long long phase[8]; // PG_PHASE_TIMING builds: warp-cycles per phase of the expand kernel
 };

@@ -114,11 +114,6 @@ struct SearchState {
     size_t region_bytes = 0;   // bytes one source may write into one inbox (per buffer)
     int xrec = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // forwarding mode: the survivors of a partition's own parents are inserted on a second stream while the main stream waits
-    // for the other partitions' parents and expands them (insert is bound by HBM transactions, expand by instruction issue)
-    cudaStream_t ins_stream = nullptr;
-    cudaEvent_t ev_split = nullptr, ev_ins = nullptr;
-    bool overlap_insert = false;
     // optional per-launch timing: event triples (before select, between, after expand), harvested at every sync
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -1521,8 +1516,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
 #endif
 template <int KEYW, int VALW>
 __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_constant__ DevSearch d, const unsigned long long *__restrict__ recs,
-                                                        const unsigned long long *__restrict__ n_ptr, unsigned long long n_max,
-                                                        const unsigned long long *__restrict__ begin_ptr)
+                                                        const unsigned long long *__restrict__ n_ptr, unsigned long long n_max)
 {
     typedef typename ValT<VALW>::T T;
     constexpr int XW = KEYW == 1 ? 3 : 4;
@@ -1539,8 +1533,7 @@ __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_c
         if (__shfl_sync(0xffffffffu, skip, 0)) return;
     }
     const long long n = (long long)min(*n_ptr & COUNT_MASK, n_max);
-    const long long begin = begin_ptr ? (long long)min(*begin_ptr, (unsigned long long)n) : 0; // records before `begin` were inserted by an earlier launch
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->table_used, (unsigned long long)(n - begin)); // records seen by insert kernels
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c->table_used, (unsigned long long)n); // records seen by insert kernels
     Counters cn = {0, 0, 0, 0, 0, 0, 0};
     int min_b = INT_MAX;
     const int prune = c->prune_limit;
@@ -1563,7 +1556,7 @@ __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_c
     };
     const long long stride = (long long)gridDim.x * blockDim.x;
     // the trip count is warp-uniform: the deferred ring is a warp-level structure
-    for (long long i0 = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * PF) {
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * PF) {
         Key<KEYW> key[PF], bkey[PF];
         unsigned long long gf[PF], h0[PF], h1[KEYW == 2 ? PF : 1];
         T lv[PF], lo[PF];
@@ -1725,13 +1718,11 @@ __global__ void __launch_bounds__(256, PG_INS_CTAS) insert_kernel(const __grid_c
     }
 }
 
-// Forwarding mode: the survivors appended so far are those of this partition's own parents.
-__global__ void mark_split_kernel(SearchCtrl *c) { c->surv_split = c->surv_n; }
-
 // P2P mode: tell every owner how many records this partition stored into its inbox this round.
-__global__ void publish_counts_kernel(const __grid_constant__ DevSearch d, unsigned long long stamp)
+__global__ void publish_counts_kernel(const __grid_constant__ DevSearch d, int stamped)
 {
     const int dst = threadIdx.x;
+    const unsigned long long stamp = stamped ? d.ctrl->xround + 1ull : 0ull;
     if (dst < d.n_parts && d.peer_counts[dst]) {
         __threadfence_system(); // the records / parents this count covers were stored by earlier kernels of this stream
         d.peer_counts[dst][d.part] = (stamp << STAMP_SHIFT) | d.outbox_count[dst];
@@ -1739,20 +1730,26 @@ __global__ void publish_counts_kernel(const __grid_constant__ DevSearch d, unsig
 }
 // Device-side wait for the other partitions' counts of this exchange round (replaces a cross-GPU barrier: a count is
 // written after the data it covers, and a partition cannot run more than one round ahead because its next round waits
-// for this partition's next stamp).  One thread per source; gives up after ~20 s (a peer failed) with an error.
-__global__ void wait_counts_kernel(const __grid_constant__ DevSearch d, unsigned long long stamp)
+// for this partition's next stamp).  One thread per source; gives up after ~20 s (a peer failed) with an error.  The
+// round counter lives in the control block and moves on here.
+__global__ void wait_counts_kernel(const __grid_constant__ DevSearch d)
 {
     const int src = threadIdx.x;
-    if (src >= d.n_parts || src == d.part) return;
-    const volatile unsigned long long *slot = d.peer_counts[d.part] + src;
-    const long long t0 = clock64();
-    while ((*slot >> STAMP_SHIFT) < stamp) {
-        if (clock64() - t0 > 40000000000ll) {
-            d.ctrl->error = 6;
-            break;
+    const unsigned long long stamp = d.ctrl->xround + 1ull;
+    __syncthreads(); // every thread has read the counter before thread 0 moves it on
+    if (src < d.n_parts && src != d.part) {
+        const volatile unsigned long long *slot = d.peer_counts[d.part] + src;
+        const long long t0 = clock64();
+        while ((*slot >> STAMP_SHIFT) < stamp) {
+            if (clock64() - t0 > 40000000000ll) {
+                d.ctrl->error = 6;
+                break;
+            }
         }
+        __threadfence_system();
     }
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) d.ctrl->xround = stamp;
 }
 
 
@@ -2133,14 +2130,12 @@ int prof_event2(pg_ctx *ctx)
 }
 
 // records at `recs`, their count in device memory at n_ptr (at most n_max)
-int launch_insert(pg_ctx *ctx, const void *recs, const unsigned long long *n_ptr, unsigned long long n_max, const unsigned long long *begin_ptr = nullptr,
-                  cudaStream_t st = nullptr)
+int launch_insert(pg_ctx *ctx, const void *recs, const unsigned long long *n_ptr, unsigned long long n_max)
 {
     SearchState *s = ctx->search;
     if (n_max == 0) return PG_OK;
-    if (!st) st = ctx->stream;
     const long long grid = std::min<long long>((long long)((n_max + 1023) / 1024), (long long)ctx->sm_count * 2 * PG_INS_CTAS);
-    PG_DISPATCH_KV(s, (insert_kernel<KW, VW><<<(unsigned)grid, 256, 0, st>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max, begin_ptr)));
+    PG_DISPATCH_KV(s, (insert_kernel<KW, VW><<<(unsigned)grid, 256, 0, ctx->stream>>>(dev_search(ctx), (const unsigned long long *)recs, n_ptr, n_max)));
     PG_CUDA(ctx, cudaGetLastError());
     return PG_OK;
 }
@@ -2176,7 +2171,7 @@ int launch_round(pg_ctx *ctx, int f_limit)
             else
                 forward_kernel<2><<<(unsigned)fgrid, 256, 0, ctx->stream>>>(ctx->dp, d, oa);
             PG_CUDA(ctx, cudaGetLastError());
-            publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(d, s->stamped ? (unsigned long long)(s->xround + 1) : 0ull);
+            publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(d, s->stamped ? 1 : 0);
             PG_CUDA(ctx, cudaGetLastError());
         }
     }
@@ -2188,19 +2183,10 @@ int launch_round(pg_ctx *ctx, int f_limit)
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     if (!s->forward) { // forwarding: the survivors are inserted after the forwarded parents have been expanded as well
         if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
-    } else if (s->overlap_insert) {
-        // ... except those of this partition's own parents: their insert (bound by HBM transactions) runs on a second stream
-        // while this one waits for the other partitions' parents and expands them (bound by instruction issue)
-        mark_split_kernel<<<1, 1, 0, ctx->stream>>>(s->d_ctrl);
-        PG_CUDA(ctx, cudaGetLastError());
-        PG_CUDA(ctx, cudaEventRecord(s->ev_split, ctx->stream));
-        PG_CUDA(ctx, cudaStreamWaitEvent(s->ins_stream, s->ev_split, 0));
-        if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_split, s->surv_cap, nullptr, s->ins_stream)) != PG_OK) return rc;
-        PG_CUDA(ctx, cudaEventRecord(s->ev_ins, s->ins_stream));
     }
     if (s->profile && (rc = prof_event(ctx)) != PG_OK) return rc;
     if (!s->forward && s->p2p && s->peer_counts[0]) {
-        publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx), s->stamped ? (unsigned long long)(s->xround + 1) : 0ull);
+        publish_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx), s->stamped ? 1 : 0);
         PG_CUDA(ctx, cudaGetLastError());
     }
     s->rounds++;
@@ -2263,7 +2249,6 @@ void pg_search_free(pg_ctx *ctx)
 {
     SearchState *s = ctx->search;
     if (!s) return;
-    if (s->ins_stream) cudaStreamSynchronize(s->ins_stream);
     cudaFree(s->d_dir);
     cudaFree(s->d_vals);
     cudaFree(s->d_buckets);
@@ -2283,9 +2268,6 @@ void pg_search_free(pg_ctx *ctx)
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     if (s->h_outbox_count) cudaFreeHost(s->h_outbox_count);
     if (s->rounds_exec) cudaGraphExecDestroy(s->rounds_exec);
-    if (s->ins_stream) cudaStreamDestroy(s->ins_stream);
-    if (s->ev_split) cudaEventDestroy(s->ev_split);
-    if (s->ev_ins) cudaEventDestroy(s->ev_ins);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
@@ -2415,9 +2397,6 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
         PG_CUDA(ctx, cudaMalloc(&s->d_trace, std::max<size_t>(1u << 16, (total + 64) * 4)));
     }
     PG_CUDA(ctx, cudaEventCreate(&s->ev0));
-    PG_CUDA(ctx, cudaStreamCreateWithFlags(&s->ins_stream, cudaStreamNonBlocking));
-    PG_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_split, cudaEventDisableTiming));
-    PG_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_ins, cudaEventDisableTiming));
     PG_CUDA(ctx, cudaEventCreate(&s->ev1));
     {
         // live parents: at most one per popped entry; survivors: at most every successor of every live parent
@@ -2431,7 +2410,6 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     if (cfg->n_parts > 1) {
         s->forward = cfg->reserved == 2;
         s->merge_expand = s->forward && getenv("PG_MERGE_EXPAND") && atoi(getenv("PG_MERGE_EXPAND")) != 0;
-        s->overlap_insert = s->forward && !s->merge_expand && !(getenv("PG_OVERLAP_INSERT") && atoi(getenv("PG_OVERLAP_INSERT")) == 0);
         if (s->forward) {
             // parent forwarding: a destination receives at most every live parent of the round
             s->outbox_cap = (uint64_t)s->batch_target + UNIT;
@@ -2554,6 +2532,13 @@ extern "C" int pg_search_profile(pg_ctx *ctx, int enable)
     return PG_OK;
 }
 
+extern "C" int pg_search_note_rounds(pg_ctx *ctx, int64_t delta)
+{
+    if (!ctx || !ctx->search) return ctx ? pg_fail(ctx, PG_ERR_STATE, "pg_search_begin has not run") : PG_ERR_ARG;
+    ctx->search->rounds += delta;
+    return PG_OK;
+}
+
 extern "C" int pg_search_set_peers(pg_ctx *ctx, void *const *peer_inbox, int n)
 {
     if (!ctx || !ctx->search || !peer_inbox) return PG_ERR_ARG;
@@ -2593,7 +2578,7 @@ extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     if (s->stamped) { // data-flow synchronisation: wait on the device for every source's count of this exchange round
-        wait_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx), (unsigned long long)(s->xround + 1));
+        wait_counts_kernel<<<1, 64, 0, ctx->stream>>>(dev_search(ctx));
         PG_CUDA(ctx, cudaGetLastError());
     }
     if (s->profile && (rc = prof_event2(ctx)) != PG_OK) return rc;
@@ -2602,12 +2587,7 @@ extern "C" int pg_search_insert_inbox_async(pg_ctx *ctx)
         // the round's survivors: those of its own parents and of the forwarded ones
         PG_DISPATCH_KV(s, (rc = launch_expand_round_k<KW, VW>(ctx, ctx->stream, true)));
         if (rc != PG_OK) return rc;
-        if (s->overlap_insert) { // the own parents' survivors went in on the second stream: only the forwarded parents' are left
-            PG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_ins, 0));
-            if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap, &s->d_ctrl->surv_split)) != PG_OK) return rc;
-        } else if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) {
-            return rc;
-        }
+        if ((rc = launch_insert(ctx, s->d_surv, &s->d_ctrl->surv_n, s->surv_cap)) != PG_OK) return rc;
     } else {
         const DevSearch d = dev_search(ctx);
         for (int src = 0; src < s->cfg.n_parts; src++) {

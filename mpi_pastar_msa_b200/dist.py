@@ -117,6 +117,7 @@ class CudaEngineP2P(CudaEngine):
         self.device_sync = os.environ.get("PG_DEVICE_SYNC", "1") != "0"
         if self.device_sync:
             gpu.search_set_device_sync(True)
+        self.rounds_done, self._graph, self._graph_key = 0, None, None
         self.sent = self._wrap64(gpu.search_outbox_counts_dev(), n_parts)   # this round's records per destination
         self.sent_total = torch.zeros(1, dtype=torch.int64, device=self.device)
         torch.cuda.synchronize()
@@ -137,6 +138,52 @@ class CudaEngineP2P(CudaEngine):
         if not self.device_sync:
             self.hdl.barrier(channel=0)        # every partition's stores of this round are complete and visible
         self.g.search_insert_inbox_async()     # (device sync: waits for the sources' counts first) dedupe + push; flips the buffers
+        self.rounds_done += 1
+
+    GRAPH_ROUNDS = 8
+
+    def rounds(self, f_limit, dist, n):
+        """n rounds.  With device-side synchronisation a round is the same launches with the same arguments every second
+        round (the double-buffered inboxes alternate; the exchange stamp lives in the device control block), so groups
+        of GRAPH_ROUNDS rounds are captured once as a CUDA graph and replayed: no launch gaps between the nine small
+        launches of a round.  Per-launch profiling, a changed f limit and odd leftovers take the plain path."""
+        torch = self.torch
+        use_graph = (self.device_sync and n >= self.GRAPH_ROUNDS and not getattr(self.g, "profiling", False)
+                     and os.environ.get("PG_NO_GRAPH") is None and self.rounds_done >= 2)
+        done = 0
+        if use_graph:
+            if self._graph is None or self._graph_key != (f_limit, self.rounds_done & 1):
+                if (self.rounds_done & 1) != 0:  # graphs start on an even round: the buffer halves repeat with period 2
+                    self.round_and_exchange(f_limit, dist)
+                    done += 1
+                if n - done >= self.GRAPH_ROUNDS:
+                    self._capture(f_limit, dist)
+            while self._graph is not None and self._graph_key == (f_limit, self.rounds_done & 1) and n - done >= self.GRAPH_ROUNDS:
+                self._graph.replay()
+                self.rounds_done += self.GRAPH_ROUNDS
+                self.g.search_note_rounds(self.GRAPH_ROUNDS)
+                done += self.GRAPH_ROUNDS
+        for _ in range(n - done):
+            self.round_and_exchange(f_limit, dist)
+
+    def _capture(self, f_limit, dist):
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        graph = torch.cuda.CUDAGraph()
+        before = self.rounds_done
+        with torch.cuda.graph(graph, stream=side):
+            self.g.set_stream(side.cuda_stream)   # the library launches on the capturing stream
+            for _ in range(self.GRAPH_ROUNDS):
+                self.round_and_exchange(f_limit, dist)
+        self.g.set_stream(cur.cuda_stream)
+        cur.wait_stream(side)
+        # capturing launched nothing: the host-side round bookkeeping moves back (GRAPH_ROUNDS is even, so the buffer half
+        # the library would use next is unchanged)
+        self.rounds_done = before
+        self.g.search_note_rounds(-self.GRAPH_ROUNDS)
+        self._graph, self._graph_key = graph, (f_limit, before & 1)
 
     def status(self):
         self.g.search_sync()
@@ -179,13 +226,17 @@ class PartitionedSearch:
     def step(self, f_limit=INT_MAX, rounds=1):
         """`rounds` rounds, then one status exchange; returns (global min open f, global best goal g, global counters)."""
         t, dist = self.torch, self.dist
-        for _ in range(rounds):
-            if hasattr(self.e, "round_and_exchange"):
-                self.e.round_and_exchange(f_limit, dist)
-            else:
-                outboxes = self.e.round(f_limit)
-                self.e.insert(self.exchange(outboxes))
-            self.rounds += 1
+        if hasattr(self.e, "rounds"):
+            self.e.rounds(f_limit, dist, rounds)  # device-driven, groups of rounds replayed as a CUDA graph
+            self.rounds += rounds
+        else:
+            for _ in range(rounds):
+                if hasattr(self.e, "round_and_exchange"):
+                    self.e.round_and_exchange(f_limit, dist)
+                else:
+                    outboxes = self.e.round(f_limit)
+                    self.e.insert(self.exchange(outboxes))
+                self.rounds += 1
         if hasattr(self.e, "round_and_exchange"):
             self.bytes_sent = self.e.bytes_sent
         mn, best, cnt = self.e.status()
