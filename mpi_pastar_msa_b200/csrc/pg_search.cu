@@ -2933,16 +2933,21 @@ extern "C" int pg_multi_search(pg_ctx *const *ctxs, int n_gpus, const pg_search_
         for (std::thread &t : th) t.join();
         for (int i = 0; i < G; i++) MG_CHECK(i, brc[i]);
     }
+    // Device-side data-flow synchronisation (default): the counts carry the exchange round and the receiver waits for them
+    // on the device, so a round needs no host hand-shake and a group of rounds replays as a CUDA graph.  PG_DEVICE_SYNC=0:
+    // the event edges below (one cudaStreamWaitEvent per peer and round, recorded / waited for by the host threads).
+    const bool stamped = !(getenv("PG_DEVICE_SYNC") && atoi(getenv("PG_DEVICE_SYNC")) == 0);
     for (int i = 0; i < G; i++) {
         MG_CHECK(i, pg_search_set_peers(ctxs[i], inbox.data(), G));
         MG_CHECK(i, pg_search_set_peer_counts(ctxs[i], counts.data(), G, 2));
+        if (stamped) MG_CHECK(i, pg_search_set_device_sync(ctxs[i], 1));
     }
 
     // ---- rounds.  One host thread per device runs that device's whole loop (the reference: one worker thread per
     // partition, PAStar.cpp:650-651).  Inside a round a thread only waits, spinning on a host flag, until its peers have
     // RECORDED this round's "forwarded" event - the wait for the event itself happens on the GPU stream - and the
     // threads meet at a host barrier for the stop test every few rounds.
-    const int per_sync = cfg.rounds_per_sync > 0 ? cfg.rounds_per_sync : 4;
+    const int per_sync = cfg.rounds_per_sync > 0 ? cfg.rounds_per_sync : (stamped ? 8 : 4);
     int best = INT_MAX, min_open = INT_MAX;
     bool finished = false;
     std::vector<pg_result> pr(G);
@@ -2982,10 +2987,58 @@ extern "C" int pg_multi_search(pg_ctx *const *ctxs, int n_gpus, const pg_search_
             };
             int sense = 0, my_best = INT_MAX;
             long round = 0;
+            // stamped mode: a group of per_sync rounds (even: the double-buffered inboxes repeat with period 2) is captured
+            // once per value of the goal bound and replayed; the first group runs as plain launches (per-device kernel
+            // attributes are set on first use)
+            cudaGraphExec_t exec = nullptr;
+            int exec_best = 0;
+            const bool graph_ok = stamped && (per_sync % 2) == 0 && !getenv("PG_NO_GRAPH");
+            struct ExecGuard {
+                cudaGraphExec_t &e;
+                ~ExecGuard()
+                {
+                    if (e) cudaGraphExecDestroy(e);
+                }
+            } guard{exec};
             for (;;) {
-                for (int r = 0; r < per_sync; r++, round++) {
+                bool replayed = false;
+                if (graph_ok && round >= per_sync) {
+                    if (cudaSetDevice(ctxs[i]->device) != cudaSuccess) return bail(pg_fail(ctxs[i], PG_ERR_CUDA, "cudaSetDevice failed"));
+                    if (exec && exec_best != my_best) {
+                        cudaGraphExecDestroy(exec);
+                        exec = nullptr;
+                    }
+                    if (!exec) {
+                        if (cudaStreamBeginCapture(ctxs[i]->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+                            return bail(pg_fail(ctxs[i], PG_ERR_CUDA, "cudaStreamBeginCapture failed"));
+                        int e = PG_OK;
+                        for (int r = 0; r < per_sync && e == PG_OK; r++) {
+                            e = pg_search_round_async(ctxs[i], my_best);
+                            if (e == PG_OK) e = pg_search_insert_inbox_async(ctxs[i]);
+                        }
+                        cudaGraph_t graph = nullptr;
+                        const cudaError_t ce = cudaStreamEndCapture(ctxs[i]->stream, &graph);
+                        if (e != PG_OK) return bail(e);
+                        if (ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+                            if (graph) cudaGraphDestroy(graph);
+                            return bail(pg_fail(ctxs[i], PG_ERR_CUDA, "capturing a group of rounds failed"));
+                        }
+                        cudaGraphDestroy(graph);
+                        pg_search_note_rounds(ctxs[i], -per_sync); // captured, not run
+                        exec_best = my_best;
+                    }
+                    if (cudaGraphLaunch(exec, ctxs[i]->stream) != cudaSuccess) return bail(pg_fail(ctxs[i], PG_ERR_CUDA, "cudaGraphLaunch failed"));
+                    pg_search_note_rounds(ctxs[i], per_sync);
+                    round += per_sync;
+                    replayed = true;
+                }
+                for (int r = 0; r < per_sync && !replayed; r++, round++) {
                     int e = pg_search_round_async(ctxs[i], my_best); // parents and counts are on their way when the event fires
                     if (e != PG_OK) return bail(e);
+                    if (stamped) { // the receiver waits for the counts on the device
+                        if ((e = pg_search_insert_inbox_async(ctxs[i])) != PG_OK) return bail(e);
+                        continue;
+                    }
                     cudaEvent_t mine = (round & 1) ? ev2[i] : ev[i];
                     if (cudaEventRecord(mine, ctxs[i]->stream) != cudaSuccess) return bail(pg_fail(ctxs[i], PG_ERR_CUDA, "cudaEventRecord failed"));
                     recorded[i].store(round, std::memory_order_release);
