@@ -202,7 +202,7 @@ class PartitionedSearch:
         self.max_expansions = max_expansions
         self.rounds = 0
         self.bytes_sent = 0
-        self.rounds_per_status = 4
+        self.rounds_per_status = 8  # one graph-replayed group (CudaEngineP2P.GRAPH_ROUNDS) between status exchanges
 
     def _dev(self):
         return getattr(self.e, "device", self.torch.device("cpu"))
