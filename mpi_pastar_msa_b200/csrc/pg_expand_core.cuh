@@ -125,15 +125,12 @@ __device__ __forceinline__ void pg_expand_prepare(const DevProblem &p, const Pai
             const int pr = e >> 2, dx = e & 1, dy = (e >> 1) & 1;
             const int x = meta->pa[pr], y = meta->pb[pr];
             const int w = meta->w[pr];
-            int c;
-            if (dx & dy)
-                c = cv[j]; // match / mismatch
-            else if (dx)
-                c = ((parenti >> y) & 1) ? p.gap_open : p.gap_ext; // gap in y, Node.cpp:140,149-151
-            else if (dy)
-                c = ((parenti >> x) & 1) ? p.gap_open : p.gap_ext; // gap in x
-            else
-                c = p.gap_gap; // Node.cpp:142
+            // match / mismatch (both move); a gap in the sequence that stays (Node.cpp:140,149-151: opened if that
+            // sequence moved into the parent, extended otherwise); gap-gap (Node.cpp:142).  dx and dy are the same for all
+            // of a lane's entries (e = sub + j * LP), so this is selects, not branches.
+            const int stays = dx ? y : x;
+            const int gapc = ((parenti >> stays) & 1) ? p.gap_open : p.gap_ext;
+            const int c = (dx & dy) ? cv[j] : ((dx | dy) ? gapc : p.gap_gap);
             s_lutg[e] = c * w;
             s_luth[e] = tv[j] * w;
         }

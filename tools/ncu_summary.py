@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (read here, no GPU): key counters + the source lines with the most stall samples.
-usage: python tools/ncu_summary.py report.ncu-rep [n_lines]"""
+usage: python tools/ncu_summary.py report.ncu-rep [n_lines] [byinst]   (byinst: rank the lines by instructions executed)"""
 import collections, csv, io, subprocess, sys
 
 rep = sys.argv[1]
@@ -49,5 +49,8 @@ for r in rows:
     a[0] += smp; a[1] += ins; a[2] = d.get("Source", "").strip()[:110]
     tot += smp
 print("total samples", tot)
-for (f, ln), (smp, ins, text) in sorted(agg.items(), key=lambda x: -x[1][0])[:nl]:
+byinst = len(sys.argv) > 3 and sys.argv[3] == "byinst"
+if byinst:
+    print("total instructions", sum(a[1] for a in agg.values()))
+for (f, ln), (smp, ins, text) in sorted(agg.items(), key=lambda x: -x[1][1 if byinst else 0])[:nl]:
     print("  %6d %5.1f%% %-22s:%-5d inst=%-9d %s" % (smp, 100.0 * smp / max(1, tot), f, ln, ins, text))
