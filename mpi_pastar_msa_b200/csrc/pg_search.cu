@@ -1042,7 +1042,11 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     constexpr int GROUPS = 256 / C::LP;
     constexpr int GPW = 32 / C::LP; // parent groups per warp
     constexpr int NI = 1 << C::IB;
+#ifdef PG_PFMAX
+    constexpr int PFMAX = PG_PFMAX;
+#else
     constexpr int PFMAX = (KEYW == 1 && N < 14) ? 8 : 4; // N >= 14: the HH tables leave less shared memory for the stash
+#endif
     constexpr int PF = NI < PFMAX ? NI : PFMAX; // successors whose table loads are in flight together, per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairMeta *meta = reinterpret_cast<PairMeta *>(smem_raw);
@@ -1998,10 +2002,18 @@ int launch_expand_round(pg_ctx *ctx, cudaStream_t st, bool inbox)
     constexpr int GROUPS = 256 / C::LP;
     constexpr int XW = KEYW == 1 ? 3 : 4;
     constexpr int NI = 1 << C::IB;
+#ifdef PG_PFMAX
+    constexpr int PFMAX = PG_PFMAX;
+#else
     constexpr int PFMAX = (KEYW == 1 && N < 14) ? 8 : 4;
+#endif
     constexpr int PF = NI < PFMAX ? NI : PFMAX; // as in the kernel
     const size_t smem = ((sizeof(PairMeta) + 15) & ~size_t(15)) + sizeof(Key<KEYW>) * C::H +
-                        sizeof(int) * (size_t)GROUPS * C::GROUP_INTS + (size_t)PF * 256 * (VALW + 12);
+                        sizeof(int) * (size_t)GROUPS * C::GROUP_INTS + (size_t)PF * 256 * (VALW + 12)
+#ifdef PG_EXTRA_SMEM
+                        + PG_EXTRA_SMEM
+#endif
+                        ;
     // per-device state (cudaFuncSetAttribute applies to the current device only): cached per context and kernel mode
     int &occ = ctx->occ_expand_probe[MODE == 2 && !LOOPOWN ? 3 : MODE];
     if (!occ) {
