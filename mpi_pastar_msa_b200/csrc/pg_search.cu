@@ -262,6 +262,9 @@ struct DevSearch {
     unsigned long long live_cap;
     unsigned long long *surv;     // local survivors of the round
     unsigned long long surv_cap;
+    // expand kernel, one-word keys with at most 4 loop bits (N <= 9): key offset of every high mask, read as a constant-bank
+    // operand of the add instead of a shared-memory load per successor
+    unsigned long long keyhigh[16];
 };
 
 struct Counters { // per thread, flushed once per kernel
@@ -1088,6 +1091,14 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
     if (MULTI) s_mod[threadIdx.x & 255] = (unsigned char)((threadIdx.x & 255) % (unsigned)d.n_parts);
     __syncthreads();
 
+    // key offset of a high mask: a kernel parameter where the table is small (see DevSearch::keyhigh), else shared memory
+    auto keyhi = [&](int high) -> Key<KEYW> {
+        if constexpr (KEYW == 1 && C::HB <= 4) {
+            return Key<KEYW>{d.keyhigh[high]};
+        } else {
+            return s_keyhigh[high];
+        }
+    };
     const int grp = threadIdx.x / C::LP, sub = threadIdx.x % C::LP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned gmask = C::LP == 32 ? 0xffffffffu : (((1u << C::LP) - 1u) << (lane & ~(C::LP - 1)));
@@ -1170,7 +1181,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     if ((slowmask >> j) & 1u) {
                         const uint32_t hit = s_ps[j * 256 + threadIdx.x];
                         const int high = pend_hb + j;
-                        const Key<KEYW> key = pend_klow.plus(s_keyhigh[high]);
+                        const Key<KEYW> key = pend_klow.plus(keyhi(high));
                         q[0] = key.lo;
                         if constexpr (KEYW == 2) q[1] = key.hi;
                         q[KEYW] = ((unsigned long long)(unsigned)s_pg[j * 256 + threadIdx.x] << 32) | (unsigned)s_pf[j * 256 + threadIdx.x];
@@ -1379,7 +1390,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                     if constexpr (SEND) {
                         if (obase) { // lane-uniform owner elsewhere: record j of this lane's reservation (move mask 0 = hole)
                             unsigned long long *r = obase + j * XW;
-                            const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                            const Key<KEYW> key = klow.plus(keyhi(high));
                             r[0] = key.lo;
                             if constexpr (KEYW == 2) r[1] = key.hi;
                             r[KEYW] = ((unsigned long long)(unsigned)gn << 32) | (unsigned)fn;
@@ -1396,7 +1407,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                             }
                         }
                         if (v) {
-                            const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                            const Key<KEYW> key = klow.plus(keyhi(high));
                             const unsigned dpos = (pdir ^ (plow & (unsigned)mask)) & dlm;
                             const unsigned long long dslot = dir_home<KEYW>(d, key, dpos);
                             ls[j] = (uint32_t)dslot;
@@ -1424,7 +1435,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                             pos0 = __shfl_sync(0xffffffffu, pos0, leader);
                             if (rem && rown == dst) {
                                 unsigned long long *r = outbox_record<KEYW>(d, dst, pos0 + __popc(same & lt));
-                                const Key<KEYW> key = klow.plus(s_keyhigh[high]);
+                                const Key<KEYW> key = klow.plus(keyhi(high));
                                 r[0] = key.lo;
                                 if constexpr (KEYW == 2) r[1] = key.hi;
                                 r[KEYW] = ((unsigned long long)(unsigned)gn << 32) | (unsigned)fn;
@@ -1444,7 +1455,7 @@ __global__ void __launch_bounds__(256, PG_EXPAND_CTAS) expand_probe_kernel(const
                         const int i = cb + j;
                         const int high = (u << C::IB) | i;
                         const int mask = (high << C::A) | sub;
-                        const Key<KEYW> bkey = block_key<KEYW>(d, klow.plus(s_keyhigh[high]));
+                        const Key<KEYW> bkey = block_key<KEYW>(d, klow.plus(keyhi(high)));
                         unsigned long long w1 = 0;
                         if constexpr (KEYW == 2) w1 = h1[j];
                         uint32_t hit = PROBE_MISS;
@@ -1964,6 +1975,16 @@ DevSearch dev_search(const pg_ctx *ctx)
     d.live_cap = s->live_cap;
     d.surv = s->d_surv;
     d.surv_cap = s->surv_cap;
+    {
+        const int A = ctx->n <= 6 ? 3 : (ctx->n <= 9 ? 4 : 5), HB = ctx->n - A; // ExpCfg<N>
+        for (int hi = 0; hi < 16; hi++) {
+            unsigned __int128 k = 0;
+            if (s->keyw == 1 && HB <= 4)
+                for (int b = 0; b < HB; b++)
+                    if ((hi >> b) & 1) k += (unsigned __int128)1 << ((A + b) * ctx->dp.key_bits);
+            d.keyhigh[hi] = (unsigned long long)k;
+        }
+    }
     return d;
 }
 
