@@ -202,6 +202,10 @@ int pg_search_profile(pg_ctx *ctx, int enable);
  * library's own round counter (pg_result.rounds / pg_search_status) only sees the calls it executes: `delta` adds the
  * replayed rounds (or takes back the ones that were captured, not run). */
 int pg_search_note_rounds(pg_ctx *ctx, int64_t delta);
+/* The large device buffers of a search (value blocks, directory, open-list pool, survivor list) are kept by the library
+ * when a search ends and reused by the next search of the same size on the same device (PAStar.cpp:626-673 allocates
+ * per run; here a 16 GiB cudaMalloc + cudaFree costs more than a small search).  This gives them back to the driver. */
+void pg_release_cached_memory(void);
 /* Device pointer + record count of the outbox for partition dst (valid until the next round). */
 int pg_search_outbox(pg_ctx *ctx, int dst, void **d_records, int64_t *count);
 /* P2P mode (the fused compute + exchange variant): give every partition's inbox base as seen from THIS device

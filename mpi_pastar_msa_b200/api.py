@@ -76,6 +76,7 @@ def load_library():
         "pg_search_rounds": ([vp, C.c_int32, C.c_int32], i32),
         "pg_search_profile": ([vp, i32], i32),
         "pg_search_note_rounds": ([vp, C.c_int64], i32),
+        "pg_release_cached_memory": ([], None),
         "pg_build_pair_tables": ([vp, C.POINTER(C.c_float)], i32),
         "pg_pair_table_shape": ([vp, i32, C.POINTER(i32), C.POINTER(i32)], i32),
         "pg_copy_pair_table": ([vp, i32, vp], i32),
@@ -115,7 +116,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pg_search_note_rounds", "pg_search_set_device_sync", "pg_allow_extended_n", "pg_gpu_weights", "pg_bench_int_peak", "pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
+EXPORTS = ["pg_release_cached_memory", "pg_search_note_rounds", "pg_search_set_device_sync", "pg_allow_extended_n", "pg_gpu_weights", "pg_bench_int_peak", "pg_multi_search", "pg_search_region_bytes", "pg_search_set_peer_counts", "pg_search_round_async", "pg_search_insert_inbox_async", "pg_search_sync", "pg_bench_random_gather", "pg_search_set_peers", "pg_search_outbox_capacity", "pg_search_outbox_counts_dev", "pg_search_insert_segments_dev",
            "pg_ctx_set_stream", "pg_search_rounds", "pg_search_profile", "pg_abi_version", "pg_last_error", "pg_default_cost_table", "pg_host_weights", "pg_ctx_create", "pg_ctx_destroy",
            "pg_build_pair_tables", "pg_pair_table_shape", "pg_copy_pair_table", "pg_calculate_h", "pg_configure_hash",
            "pg_owner", "pg_expand_batch", "pg_expand_batch_dev", "pg_search", "pg_search_begin", "pg_search_round",
@@ -239,6 +240,11 @@ def host_weights(seqs):
     if rc:
         raise PastarError(rc, "pg_host_weights")
     return out
+
+
+def release_cached_memory():
+    """Give the device buffers the library keeps between searches back to the driver (pg_release_cached_memory)."""
+    load_library().pg_release_cached_memory()
 
 
 def allow_extended_n(enable=True):

@@ -40,7 +40,10 @@
 #include <cstdio>
 #include <atomic>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "pg_expand_core.cuh"
@@ -86,6 +89,7 @@ struct SearchState {
     uint32_t n_units = 0;
     PlanEntry *d_plan = nullptr;
     uint32_t plan_cap = 0;
+    size_t bytes_dir = 0, bytes_vals = 0, bytes_pool = 0, bytes_link = 0, bytes_live = 0, bytes_surv = 0; // sizes of the cached buffers
     SearchCtrl *d_ctrl = nullptr;
     SearchCtrl *h_ctrl = nullptr; // pinned
     uint32_t *d_trace = nullptr;  // backtrace output
@@ -2274,25 +2278,92 @@ void fill_counters(const SearchState *s, pg_result *r)
 
 } // namespace
 
+// ---- the large device buffers of a search (value blocks, directory, open-list pool, survivor list: tens of GB) are kept
+// for the life of the process and handed to the next search that asks for the same size on the same device: a
+// cudaMalloc + cudaFree of 16 GiB costs tens of milliseconds (more when eight processes do it at once), which is most
+// of what a sub-second job spends outside its kernels.  pg_release_cached_memory() gives everything back.
+namespace {
+constexpr size_t BIG_MIN = 64ull << 20;      // smaller buffers go straight to cudaMalloc / cudaFree
+constexpr size_t BIG_HELD_MAX = 64ull << 30; // per process; beyond it freed buffers are released
+struct BigCache {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void *> free_list;
+    size_t held = 0;
+} g_big;
+
+void big_release_all()
+{
+    std::lock_guard<std::mutex> lk(g_big.m);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &kv : g_big.free_list) {
+        cudaSetDevice(kv.first.first);
+        cudaFree(kv.second);
+    }
+    g_big.free_list.clear();
+    g_big.held = 0;
+    cudaSetDevice(cur);
+}
+
+cudaError_t big_alloc(int device, void **p, size_t bytes)
+{
+    if (bytes >= BIG_MIN) {
+        std::lock_guard<std::mutex> lk(g_big.m);
+        auto it = g_big.free_list.find({device, bytes});
+        if (it != g_big.free_list.end()) {
+            *p = it->second;
+            g_big.held -= bytes;
+            g_big.free_list.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation && g_big.held) { // make room and try once more
+        cudaGetLastError();
+        big_release_all();
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+
+// the caller has synchronised the stream(s) that used the buffer
+void big_free(int device, void *p, size_t bytes)
+{
+    if (!p) return;
+    if (bytes >= BIG_MIN) {
+        std::lock_guard<std::mutex> lk(g_big.m);
+        if (g_big.held + bytes <= BIG_HELD_MAX) {
+            g_big.free_list.insert({{device, bytes}, p});
+            g_big.held += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+} // namespace
+
+extern "C" void pg_release_cached_memory(void) { big_release_all(); }
+
 void pg_search_free(pg_ctx *ctx)
 {
     SearchState *s = ctx->search;
     if (!s) return;
-    cudaFree(s->d_dir);
-    cudaFree(s->d_vals);
+    cudaStreamSynchronize(ctx->stream); // nothing of this search is in flight when its buffers change hands
+    big_free(ctx->device, s->d_dir, s->bytes_dir);
+    big_free(ctx->device, s->d_vals, s->bytes_vals);
     cudaFree(s->d_buckets);
     cudaFree(s->d_tail);
     cudaFree(s->d_hint);
-    cudaFree(s->d_pool);
-    cudaFree(s->d_link);
+    big_free(ctx->device, s->d_pool, s->bytes_pool);
+    big_free(ctx->device, s->d_link, s->bytes_link);
     cudaFree(s->d_free);
     cudaFree(s->d_plan);
     cudaFree(s->d_ctrl);
     cudaFree(s->d_trace);
     cudaFree(s->d_outbox);
     cudaFree(s->d_outbox_count);
-    cudaFree(s->d_live);
-    cudaFree(s->d_surv);
+    big_free(ctx->device, s->d_live, s->bytes_live);
+    big_free(ctx->device, s->d_surv, s->bytes_surv);
     cudaFree(s->d_host_counts);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     if (s->h_outbox_count) cudaFreeHost(s->h_outbox_count);
@@ -2389,9 +2460,11 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     const uint64_t cap = std::max<uint64_t>(s->cap / 4, 1024); // coordinates provided for: sizes the open-list pool
 
     // ---- allocations
-    PG_CUDA(ctx, cudaMalloc(&s->d_dir, (size_t)s->dir_slots * 8 * s->keyw));
+    s->bytes_dir = (size_t)s->dir_slots * 8 * s->keyw;
+    PG_CUDA(ctx, big_alloc(ctx->device, (void **)&s->d_dir, s->bytes_dir));
     PG_CUDA(ctx, cudaMemsetAsync(s->d_dir, 0, (size_t)s->dir_slots * 8 * s->keyw, ctx->stream));
-    PG_CUDA(ctx, cudaMalloc(&s->d_vals, (size_t)s->cap * s->valw));
+    s->bytes_vals = (size_t)s->cap * s->valw;
+    PG_CUDA(ctx, big_alloc(ctx->device, (void **)&s->d_vals, s->bytes_vals));
     PG_CUDA(ctx, cudaMemsetAsync(s->d_vals, 0, (size_t)s->cap * s->valw, ctx->stream));
     PG_CUDA(ctx, cudaMalloc(&s->d_buckets, (size_t)s->f_range * 8));
     PG_CUDA(ctx, cudaMalloc(&s->d_tail, (size_t)s->f_range * 4));
@@ -2404,8 +2477,10 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
     // size; each non-empty bucket holds at least one unit.
     uint64_t units = 5 * (cap / UNIT) + (uint64_t)s->f_range + 4096; // measured: 2.7 pushes per table entry + chunk slack
     s->n_units = (uint32_t)std::min<uint64_t>(units, 0x7ffffff0ull);
-    PG_CUDA(ctx, cudaMalloc(&s->d_pool, (size_t)s->n_units * UNIT * 4));
-    PG_CUDA(ctx, cudaMalloc(&s->d_link, (size_t)s->n_units * 8));
+    s->bytes_pool = (size_t)s->n_units * UNIT * 4;
+    PG_CUDA(ctx, big_alloc(ctx->device, (void **)&s->d_pool, s->bytes_pool));
+    s->bytes_link = (size_t)s->n_units * 8;
+    PG_CUDA(ctx, big_alloc(ctx->device, (void **)&s->d_link, s->bytes_link));
     {   // free stacks: class lg can never hold more than n_units >> lg chunks
         uint32_t tot = 0;
         for (uint32_t lg = 0; lg <= MAXLG; lg++) {
@@ -2431,9 +2506,11 @@ extern "C" int pg_search_begin(pg_ctx *ctx, const pg_search_config *cfg)
         // live parents: at most one per popped entry; survivors: at most every successor of every live parent
         const uint64_t S = (1ull << ctx->n) - 1;
         s->live_cap = (uint64_t)s->batch_target + UNIT;
-        PG_CUDA(ctx, cudaMalloc(&s->d_live, (size_t)s->live_cap * (s->keyw + 1) * 8));
+        s->bytes_live = (size_t)s->live_cap * (s->keyw + 1) * 8;
+        PG_CUDA(ctx, big_alloc(ctx->device, (void **)&s->d_live, s->bytes_live));
         s->surv_cap = (uint64_t)(s->batch_target + UNIT) * S + 64;
-        PG_CUDA(ctx, cudaMalloc(&s->d_surv, (size_t)s->surv_cap * s->xrec));
+        s->bytes_surv = (size_t)s->surv_cap * s->xrec;
+        PG_CUDA(ctx, big_alloc(ctx->device, (void **)&s->d_surv, s->bytes_surv));
         PG_CUDA(ctx, cudaMalloc(&s->d_host_counts, 8 * 64));
     }
     if (cfg->n_parts > 1) {
