@@ -69,3 +69,22 @@ def test_table_capacity_error(gpu_lib):
         with pytest.raises(gpu_lib.PastarError) as e:
             G.search(table_capacity=1024, batch_target=4096)
         assert e.value.code == 4  # PG_ERR_CAPACITY, not a wrong answer
+
+
+def test_cached_buffers_are_reused_and_released(gpu_lib):
+    """The large device buffers of a search are kept by the library and handed to the next search of the same size
+    (a second job in one process must not see the first one's table contents); pg_release_cached_memory gives them back
+    and a search after that allocates afresh.  Same optimal cost every time."""
+    import torch
+    seqs = CASES["kinase"]
+    got = []
+    for step in range(3):
+        with gpu_lib.PastarGPU(seqs) as G:
+            G.build_pair_tables()
+            r = G.search(table_capacity=1 << 27, batch_target=16384, want_rows=False)  # 512 MiB of value blocks: cached
+            got.append((r["finished"], r["g"], r["closed_size"] > 0))
+        if step == 1:
+            free0 = torch.cuda.mem_get_info()[0]
+            gpu_lib.release_cached_memory()
+            assert torch.cuda.mem_get_info()[0] >= free0 + (256 << 20)  # the value blocks went back to the driver
+    assert got == [(1, 421546, True)] * 3
