@@ -361,6 +361,7 @@ def run_ours(args, rank, world):
                    "nvlink_bytes_per_step_per_gpu": (sent1 - s0) / k_steps,
                    "rank0_kernel_ms_per_step": {k: (p1[k] - p0[k]) / k_steps for k in ("select_ms", "claim_ms", "expand_ms", "insert_ms", "inbox_ms")},
                    "rank0_records_inserted_per_step": (p1["survivors"] - p0["survivors"]) / k_steps,
+                   "rank0_counts_per_step": {k: (p1[k] - p0[k]) / k_steps for k in ("pops", "expansions", "probed", "pushed", "survivors")},
                    "forward": isinstance(e, CudaEngineP2P) and e.forward, "p2p": isinstance(e, CudaEngineP2P)}
             e.end()
             return out
@@ -408,6 +409,21 @@ def run_ours(args, rank, world):
             "clocks": clocks, "gpu_launches": launches_per_step * K,
             "successors_per_sec": (dv if world == 1 else d)["generated"] / (max_ms * 1e-3)}
 
+    if world > 1:
+        # roofline of the round on rank 0 (the per-launch split of the two expand launches is not timed separately at N > 1):
+        # the algorithmic bytes of DESIGN.md 4 for claim + both expand launches + insert, over the sum of rank 0's kernel
+        # times in the profiled pass.  Forwarded parents received ~ forwarded parents sent (16 B each over NVLink).
+        hbm, how = measured_peaks()
+        n_, P_ = len(seqs), len(seqs) * (len(seqs) - 1) // 2
+        cnt, kms = r_main["rank0_counts_per_step"], r_main["rank0_kernel_ms_per_step"]
+        fwd = r_main["nvlink_bytes_per_step_per_gpu"] / 16.0 if r_main["forward"] else 0.0
+        alg = (cnt["pops"] * 20.0 + cnt["expansions"] * 16.0 + (cnt["expansions"] + fwd) * (16.0 + n_ + 16 * P_) + cnt["probed"] * 32.0
+               + cnt["survivors"] * 24.0 + cnt["survivors"] * 56.0 + cnt["pushed"] * 36.0)
+        tms = sum(kms.values())
+        line["roofline"] = {"bound": "hbm", "kernel": "search round on rank 0: claim + expand (own parents) + expand (forwarded parents) + insert",
+                            "achieved": alg / (tms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (tms * 1e-3) / 1e9 / hbm, "traffic": None,
+                            "peak_source": how, "algorithmic_bytes_per_launch": alg, "kernel_ms_per_step": tms,
+                            "note": "per-kernel roofline and ncu traffic: the N = 1 line (profiles/r02_bench_n1.json); cpu_baseline is reported at N = 1 only"}
     if world == 1:
         hbm, how = measured_peaks()
         P, S, n = G.npairs, G.S, G.n

@@ -5,7 +5,8 @@ print("%d GPU(s): %.1f M expansions/s, %.3f ms/round, e2e %.1f M/s" % (d["n_gpus
 r = d.get("roofline")
 if r:
     print("roofline: %s frac %.3f of %s GB/s, whole round %.3f, traffic %s" % (r["kernel"], r["frac"], r["peak"], r.get("whole_round_frac", 0), r.get("traffic")))
-    print("kernels (us):", {k: round(v["ms_per_step"] * 1e3, 1) for k, v in r["kernels"].items()})
+    if "kernels" in r:
+        print("kernels (us):", {k: round(v["ms_per_step"] * 1e3, 1) for k, v in r["kernels"].items()})
 x = d.get("extra", {})
 if "pair_dp" in x:
     print("pair DP: S7 %.1f GCUPS" % x["pair_dp"]["gcups"], "S8 %.1f GCUPS" % x.get("s8", {}).get("pair_dp", {}).get("gcups", 0),
