@@ -123,6 +123,20 @@ def cpu_reference_run(threads, steps, warmup, want_sample=True):
             "seconds": secs, "expansions": exps}
 
 
+def cpu_micro_baselines(seconds=2.0):
+    """SURVEY 8(d) micro-baselines on ONE host core, reference code only (oracle/_ref `micro`): PairAlign::Align GCUPS over the
+    21 S7 tables and Node::getNeigh parents/s on 4096 seeded interior parents.  Reported beside cpu_baseline, never a target."""
+    from oracle import refio
+    if not refio.available():
+        return {"unavailable": "oracle/_ref not built"}
+    r = refio.micro(s7_seqs(), seconds)
+    return {"cores": 1, "pair_align_gcups": r["dp_gcups"], "pair_align_seconds_s7": r["dp_seconds"],
+            "getneigh_parents_per_s": r["neigh_parents_per_s"],
+            "getneigh_successors_per_s": r["neigh_successors"] / r["neigh_seconds"] if r["neigh_seconds"] > 0 else None,
+            "sample": "reference PairAlign::Align over the 21 S7 tables (%d cells) and Node<7>::getNeigh over 4096 seeded interior "
+                      "parents, ~%.0f s each on one core" % (r["dp_cells"], seconds / 2)}
+
+
 def probe_reference_toolchain():
     """can the real reference (mpich + Boost + LZ4, `make` -> ./bin/pastar) be built on this box?  Its
     sources are not on the GPU box (/root/reference exists only in the build container), so even a complete toolchain could
@@ -151,6 +165,10 @@ def run_reference(args, rank, world):
             "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0, "reference_build": probe_reference_toolchain()}
+    try:
+        line["cpu_baseline"]["micro"] = cpu_micro_baselines()
+    except Exception as ex:
+        line["cpu_baseline"]["micro"] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)
 
 
@@ -617,6 +635,10 @@ def run_ours(args, rank, world):
             threads = os.cpu_count() or 1
             b = cpu_reference_run(threads, 100, 10)  # 1.5 M dequeues after 150 K warm-up: 10-30 s of CPU work
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                line["cpu_baseline"]["micro"] = cpu_micro_baselines()
+            except Exception as ex:
+                line["cpu_baseline"]["micro"] = {"error": repr(ex)}
         except Exception as ex:  # never lose the GPU numbers to a CPU-side hiccup
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
     else:
