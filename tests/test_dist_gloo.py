@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the hash-partitioned driver (exchange by owner, allreduce(min) stop, distributed backtrace)
+"""CPU, world_size 2 (and 4), gloo: the hash-partitioned driver (exchange by owner, allreduce(min) stop, distributed backtrace)
 with a TEST-ONLY engine that stands in for the CUDA kernels (oracle getNeigh + a dict as closed/open table).  The product
 engine is CudaEngine; this covers the host-side logic of the N>1 path without a GPU."""
 import heapq
@@ -148,6 +148,32 @@ def test_partitioned_search_two_ranks(name, batch):
     assert got[0]["expansions"] == got[1]["expansions"] >= 1   # allreduced totals agree on every rank
     assert got[0]["bytes_sent"] + got[1]["bytes_sent"] > 0      # successors really crossed partitions
     assert got[0]["table"] > 0 and got[1]["table"] > 0          # both partitions own part of the state space
+
+
+@pytest.mark.parametrize("name,batch", [("fam5x60", 16), ("PF08184", 2)])
+def test_partitioned_search_four_ranks(name, batch):
+    """G = 4: two owner bits (FZORDER: `(Z >> shift) & 3`), three peers per rank in the all-to-all, stop test over four partitions."""
+    from oracle import oracle as O
+    seqs = CASES[name]
+    ref = O.Problem(seqs).astar(want_rows=False)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 4
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, batch, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        res = got[r]
+        assert res["finished"] == 1 and res["g"] == ref["g"], (name, r, res["g"], ref["g"])
+        assert res["rows"] == got[0]["rows"] and res["expansions"] == got[0]["expansions"]
+    assert weighted_sp_score(seqs, O.Problem(seqs).int_weights(), got[0]["rows"]) == ref["g"]
+    assert sum(got[r]["bytes_sent"] for r in range(world)) > 0
+    assert sum(1 for r in range(world) if got[r]["table"] > 0) >= 2   # the state space is really split
 
 
 class ChainedOracleEngine(OracleEngine):
