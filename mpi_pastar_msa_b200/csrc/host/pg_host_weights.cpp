@@ -306,6 +306,8 @@ extern "C" int pg_host_weights(int n_seq, const char *const *seqs, const int *le
     std::vector<std::string> s(n);
     for (int i = 0; i < n; i++) {
         if (!seqs[i] || lens[i] < 1) return PG_ERR_ARG;
+        for (int j = 0; j < lens[i]; j++) // 'Z' (90) and above index past pam250['Z']['Z'] in the reference (Cost.h:49): its
+            if ((unsigned char)seqs[i][j] >= 90) return PG_ERR_ARG; // weights then vary with the environment; refused as in pg_ctx_create
         s[i] = "-" + std::string(seqs[i], seqs[i] + lens[i]); // WeightedSP.cpp:447
     }
     // The N(N-1)/2 pair distances (the reference's `primer`, WeightedSP.cpp:144-244) are independent of each other:

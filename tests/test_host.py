@@ -81,3 +81,42 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 src = open(os.path.join(d, f), errors="ignore").read()
                 assert "pastar_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def _weight_edge_cases():
+    import random
+    from conftest import family_seqs
+    al = "ACDEFGHIKLMNPQRSTVWY"
+    rng = random.Random(7)
+    cases = {}
+    for n in (3, 4, 5, 6, 7, 8, 9, 10, 14, 16):
+        cases["ragged%d" % n] = ["".join(rng.choice(al) for _ in range(rng.randint(1, 90))) for _ in range(n)]
+        cases["fam%d" % n] = family_seqs(n, 40 + 3 * n, 100 + n, sub=0.2, indel=0.05)
+    cases["identical4"] = ["ACDEFGHIKL"] * 4            # all pair distances 0: the neighbour-joining tie path
+    cases["identical3_len1"] = ["A"] * 3
+    cases["len1_mixed"] = ["A", "C", "DE", "F", "GHI"]
+    cases["two_groups"] = ["AAAAAAAAAA", "AAAAAAAAAC", "WWWWWWWWWW", "WWWWWWWWWY", "AAAAWWWWWW"]  # reference yields inf weights
+    cases["rare_letters"] = ["ABXXJOU", "BJXBOXAA", "UOJACD", "ACDXB"]  # letters with unset PAM rows; not 'Z': index 90 is out of the reference's table (its output then varies with the environment)
+    return cases
+
+
+@pytest.mark.parametrize("name", list(_weight_edge_cases()))
+def test_host_weights_edge_cases_vs_reference_build(name):
+    """pg_host_weights against the reference compiled in place (oracle/_ref), float bit patterns, on inputs the golden
+    file does not hold: ragged lengths down to 1, every supported N, identical sequences (zero distances), two distant
+    groups (the reference's weights overflow to inf there, and so must ours), letters with unset PAM rows."""
+    from oracle import refio
+    if not refio.available():
+        pytest.skip("oracle/_ref is built by __graft_entry__.build() where /root/reference exists")
+    seqs = _weight_edge_cases()[name]
+    ref = refio.dump(seqs)["weights"]
+    w = m.host_weights(seqs)
+    assert np.array_equal(w.view(np.uint32), ref.view(np.uint32))
+
+
+def test_host_weights_refuses_residues_outside_the_cost_table():
+    # 'Z' = index 90 reads past pam250['Z']['Z'] in the reference (Cost.h:49); refused like pg_ctx_create / pg_gpu_weights do
+    with pytest.raises(api.PastarError):
+        m.host_weights(["ACDZ", "ACDE", "ACD"])
+    with pytest.raises(api.PastarError):
+        m.host_weights(["ACDe", "ACDE", "ACD"])   # lowercase: also outside the 90 x 90 table
