@@ -48,3 +48,50 @@ def test_astar_and_partitioned_driver():
     assert a["g"] == r["g"] and a["expansions"] == r["expansions"] and a["generated"] == r["generated"]
     p = R.pastar(seqs, 4)  # T-thread hash-partitioned driver (PAStar.cpp:319-547 restated): same optimal cost
     assert p["finished"] == 1 and p["g"] == r["g"]
+
+
+def _edge_inputs():
+    import random
+    al = "ACDEFGHIKLMNPQRSTVWY"
+    rng = random.Random(11)
+    return {
+        "len1_mixed": ["A", "C", "DE", "F", "GHI"],                     # sequences of one residue: 2-row tables
+        "identical3": ["ACDEFG"] * 3,                                    # zero-cost diagonal, all ties
+        "ragged6": ["".join(rng.choice(al) for _ in range(l)) for l in (1, 2, 17, 3, 40, 9)],
+        "unset_pam_rows": ["ABXXJOU", "BJXBOXAA", "UOJACD", "ACDXB"],    # B, J, O, U, X cost 0 against everything
+        "ragged9": ["".join(rng.choice(al) for _ in range(rng.randint(1, 12))) for _ in range(9)],
+        "ragged10": ["".join(rng.choice(al) for _ in range(rng.randint(1, 8))) for _ in range(10)],
+    }
+
+
+@pytest.mark.parametrize("name", list(_edge_inputs()))
+def test_edge_inputs(name):
+    """Tables, weights, calculate_h, getNeigh records and owners on degenerate inputs, parents on the lattice borders
+    (start, goal, goal - 1, alternating corners) included; serial A* counters where the search is small."""
+    import random
+    seqs = _edge_inputs()[name]
+    n = len(seqs)
+    d = R.dump(seqs)
+    assert np.array_equal(O.weights(seqs).view(np.uint32), d["weights"].view(np.uint32))
+    k = 0
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            assert np.array_equal(O.pair_table(seqs[i], seqs[j]), d["tables"][k])
+            k += 1
+    P = O.Problem(seqs)
+    rng = random.Random(3)
+    fin = [len(s) for s in seqs]
+    pos = [[0] * n, fin[:], [max(0, f - 1) for f in fin], [f if i % 2 else 0 for i, f in enumerate(fin)]]
+    pos += [[rng.randint(0, f) for f in fin] for _ in range(4)]
+    pos = np.array(pos, dtype=np.uint16)
+    g = np.arange(len(pos), dtype=np.int32) * 37
+    par = np.array([(1 << n) - 1, 1, 2, 3, 1, (1 << n) - 2, 5, 4], dtype=np.int32)
+    for (vs, ht, sh) in [(1, "FZORDER", 12), (8, "FZORDER", 0), (4, "PZORDER", 1), (3, "FSUM", 2), (5, "PSUM", 0)]:
+        ref = R.neigh(seqs, pos, g, par, vs, ht, sh)
+        for q in range(len(pos)):
+            mine = P.get_neigh(pos[q], g[q], par[q], vs, ht, sh)
+            assert int(g[q]) + P.calculate_h(pos[q]) == ref[q][0]
+            assert np.array_equal(mine, ref[q][1])
+    if n <= 5:
+        a, r = P.astar(want_rows=False), R.astar(seqs)
+        assert (a["g"], a["expansions"], a["generated"]) == (r["g"], r["expansions"], r["generated"])
