@@ -152,7 +152,11 @@ class HeuristicHPair {
         // the pair loop of weightAltschulsRationale2 runs on the device; very long sequences take the host routine
         int rc = pg_gpu_weights(n, ptr.data(), len.data(), device, flat.data(), nullptr);
         if (rc == PG_ERR_UNSUPPORTED) rc = pg_host_weights(n, ptr.data(), len.data(), flat.data());
-        if (rc != PG_OK) throw GpuError(rc, "pair weights (pg_gpu_weights / pg_host_weights) failed");
+        if (rc != PG_OK)
+            throw GpuError(rc, std::string("pair weights (pg_gpu_weights / pg_host_weights) failed: ") +
+                                   (rc == PG_ERR_CUDA  ? "CUDA failure or no CUDA device (there is no CPU fallback)"
+                                    : rc == PG_ERR_ARG ? "bad input (empty sequence, or a residue outside the 90x90 cost table)"
+                                                       : "status " + std::to_string(rc)));
         rows.resize(n);
         for (int i = 0; i < n; i++) rows[i] = flat.data() + (size_t)i * n;
         weightMatrix = rows.data();

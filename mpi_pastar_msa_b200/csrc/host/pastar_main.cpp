@@ -80,8 +80,32 @@ static int options_core(int argc, char *argv[], std::string &filename, PAStarOpt
         const std::string ll = std::string("--") + l;
         return (a.size() >= 2 && a[0] == '-' && a[1] == s) || a == ll || a.compare(0, ll.size() + 1, ll + "=") == 0;
     };
+    // Boost.ProgramOptions' default style lets a long option be shortened to any unambiguous prefix ("--thr 4", "--hash_t=FSUM")
+    static const char *const long_names[] = {"version", "help", "memory_debug", "threads", "hash_shift", "hash_type", "gpus",
+                                             "batch", "table_capacity", "max_expansions", "metrics_json"};
+    auto canonical = [&](const std::string &arg) -> std::string {
+        if (arg.size() < 3 || arg.compare(0, 2, "--") != 0) return arg;
+        const size_t eq = arg.find('=');
+        const std::string name = arg.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+        const char *hit = nullptr;
+        int hits = 0;
+        for (const char *l : long_names) {
+            if (name == l) return arg;
+            if (!name.empty() && std::string(l).compare(0, name.size(), name) == 0) {
+                hit = l;
+                hits++;
+            }
+        }
+        if (hits > 1) throw std::invalid_argument("option '--" + name + "' is ambiguous");
+        if (hits == 0) throw std::invalid_argument("unrecognised option '--" + name + "'");
+        return std::string("--") + hit + (eq == std::string::npos ? "" : arg.substr(eq));
+    };
+    auto is_long = [](const std::string &a, const char *l) {
+        const std::string ll = std::string("--") + l;
+        return a == ll || a.compare(0, ll.size() + 1, ll + "=") == 0;
+    };
     for (int i = 1; i < argc; i++) {
-        const std::string a = argv[i];
+        const std::string a = canonical(argv[i]);
         if (a == "-v" || a == "--version") version = true;
         else if (a == "-h" || a == "--help") help = true;
         else if (a == "--memory_debug") memory_debug = true;
@@ -89,10 +113,10 @@ static int options_core(int argc, char *argv[], std::string &filename, PAStarOpt
         else if (is(a, 's', "hash_shift")) opt.hash_shift = std::stoi(value(i, a, "hash_shift"));
         else if (is(a, 'y', "hash_type")) hash_read = value(i, a, "hash_type");
         else if (is(a, 'g', "gpus")) opt.gpus = std::stoi(value(i, a, "gpus"));
-        else if (a.compare(0, 7, "--batch") == 0) opt.batch = std::stoll(value(i, a, "batch"));
-        else if (a.compare(0, 16, "--table_capacity") == 0) opt.table_capacity = std::stoll(value(i, a, "table_capacity"));
-        else if (a.compare(0, 16, "--max_expansions") == 0) opt.max_expansions = std::stoll(value(i, a, "max_expansions"));
-        else if (a.compare(0, 14, "--metrics_json") == 0) opt.metrics_json = value(i, a, "metrics_json");
+        else if (is_long(a, "batch")) opt.batch = std::stoll(value(i, a, "batch"));
+        else if (is_long(a, "table_capacity")) opt.table_capacity = std::stoll(value(i, a, "table_capacity"));
+        else if (is_long(a, "max_expansions")) opt.max_expansions = std::stoll(value(i, a, "max_expansions"));
+        else if (is_long(a, "metrics_json")) opt.metrics_json = value(i, a, "metrics_json");
         else if (!a.empty() && a[0] == '-' && a.size() > 1) throw std::invalid_argument("unrecognised option '" + a + "'");
         else {
             filename = a; // file.fasta is position independent

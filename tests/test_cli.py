@@ -38,12 +38,32 @@ def test_version_help_and_errors(tmp_path):
     assert r.returncode == 1 and "Invalid argument" in r.stderr.decode()
 
 
+def test_option_forms_of_program_options(tmp_path):
+    """msa_options.cpp:30-75 parses with Boost.ProgramOptions' default style: `--opt=v`, `--opt v`, `-o v`, `-ov`, options after
+    the positional file, and long options shortened to an unambiguous prefix.  A run that gets past the parser either
+    solves the input (GPU box) or ends with -1 at the first device call (no GPU); a parse error ends with 1."""
+    fa = tmp_path / "a.fasta"
+    write_fasta(str(fa), CASES["PF08184"])
+    for args in (["--threads=2"], ["--threads", "2"], ["-t2"], ["-t", "2"], ["--hash_type=FSUM"], ["-yPSUM"], ["-s3"],
+                 ["--hash_shift=3"], ["--thr", "2"], ["--hash_t=PZORDER", "--hash_s", "3"], ["--memory_debug"]):
+        for argv in (args + [str(fa)], [str(fa)] + args):
+            r = run(argv)
+            assert r.returncode in (0, 255), (argv, r.returncode, r.stderr.decode())
+            assert "Invalid argument" not in r.stderr.decode()
+    for args, msg in ((["--hash", "3"], "ambiguous"), (["--batchx", "3"], "unrecognised option"), (["-t"], "Invalid argument"),
+                      (["-t", "abc"], "Invalid argument"), (["--hash_type=fsum"], "Invalid argument")):
+        r = run(args + [str(fa)])
+        assert r.returncode == 1 and msg in r.stderr.decode(), (args, r.returncode, r.stderr.decode())
+    assert run(["--ver"]).stdout.decode() == "msa_pastar, version 1.0\n"
+
+
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_gpu(tmp_path):
     fa = tmp_path / "a.fasta"
     write_fasta(str(fa), CASES["PF08184"])
     r = run([str(fa)])
     assert r.returncode == 255 and "Running fatal error" in r.stderr.decode()  # -1, as the reference on an exception
+    assert "no CUDA device" in r.stderr.decode()
 
 
 @pytest.mark.gpu
