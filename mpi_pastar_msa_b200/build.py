@@ -86,6 +86,14 @@ def build(force=False, verbose=False, ptxas_info=False):
     tbin = os.path.join(HERE, "bin", "boundary_test")
     if os.path.exists(tsrc) and not VARIANT and (force or _newer([tsrc] + hdrs + [LIB], tbin)):
         _run([CXX] + CXX_FLAGS + [tsrc, "-o", tbin, "-L" + os.path.dirname(LIB), "-lpastar_gpu", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"], verbose)
+    # CPU-only check program of the host mirror (FASTA reader, similarity / alignment printer): the CLI's translation unit
+    # with its main renamed, plus tests/cpp/host_cpu_test.cpp
+    hsrc = os.path.join(ROOT, "tests", "cpp", "host_cpu_test.cpp")
+    hbin = os.path.join(HERE, "bin", "host_cpu_test")
+    if os.path.exists(hsrc) and cli and not VARIANT and (force or _newer([hsrc] + cli + hdrs + [LIB], hbin)):
+        cobj = os.path.join(OBJ, "pastar_main_nomain.o")
+        _run([CXX] + CXX_FLAGS + ["-Dmain=pastar_cli_main", "-c", cli[0], "-o", cobj], verbose)
+        _run([CXX] + CXX_FLAGS + [hsrc, cobj, "-o", hbin, "-L" + os.path.dirname(LIB), "-lpastar_gpu", "-Wl,-rpath,$ORIGIN/../lib", "-pthread"], verbose)
     return LIB
 
 

@@ -45,6 +45,9 @@
 #include "include/Sequences.h"
 #include "include/max_seq_helper.h"
 #include "include/read_fasta.h"
+#include "include/backtrace.h"
+#include <list>
+#include <unistd.h>
 
 namespace {
 
@@ -608,6 +611,22 @@ int micro_run(double seconds)
     return 0;
 }
 
+// The reference's own printer (backtrace.cpp:135-191, through print_entire_backtrace as PAStarDistributedBacktrace.cpp:211
+// calls it) over aligned rows read from a text file: N lines of equal length.
+template <int N>
+int print_run(const char *rows_path)
+{
+    std::ifstream in(rows_path);
+    std::list<char> alignments[N];
+    for (int i = 0; i < N; i++) {
+        std::string line;
+        if (!std::getline(in, line)) return 1;
+        alignments[i].assign(line.begin(), line.end());
+    }
+    print_entire_backtrace<N>(alignments);
+    return 0;
+}
+
 int usage()
 {
     std::cerr << "usage: pastar_ref dump  <fasta> <out.bin>\n"
@@ -615,7 +634,9 @@ int usage()
                  "       pastar_ref owner <fasta> <coords.bin> <out.bin> <vec_size> <HASH> <shift>\n"
                  "       pastar_ref astar <fasta> [budget]\n"
                  "       pastar_ref pastar <fasta> <threads> [budget] [HASH] [shift] [warm_pops]\n"
-                 "       pastar_ref micro <fasta> [seconds]\n";
+                 "       pastar_ref micro <fasta> [seconds]\n"
+                 "       pastar_ref seqs  <fasta>\n"
+                 "       pastar_ref print <fasta> <rows.txt>\n";
     return 2;
 }
 
@@ -627,6 +648,23 @@ int main(int argc, char **argv)
     std::string cmd = argv[1];
     if (read_fasta_file(argv[2]) != 0) return 1;
     int n = Sequences::get_seq_num();
+    if (cmd == "seqs") { // what read_fasta_file (read_fasta.cpp:8-56) made of the file: count, then one sequence per line
+        std::cout << n << "\n";
+        for (int i = 0; i < n; i++) std::cout << Sequences::getInstance()->get_seq(i) << "\n";
+        std::cout.flush();
+        _exit(0); // the heuristic was never initialised: skip the singletons' destructors
+    }
+    if (cmd == "print") {
+        if (argc < 4) return usage();
+#define DISPATCH_PRINT_RC(X)         \
+    case X:                          \
+        rc = print_run<X>(argv[3]); \
+        break;
+        int rc = 1;
+        switch (n) { MAX_NUM_SEQ_HELPER(DISPATCH_PRINT_RC) }
+        std::cout.flush();
+        _exit(rc);
+    }
     // stdout of init ("Starting pairwise alignments..." + timer) is noise for
     // the JSON consumers: send it to stderr.
     std::streambuf *keep = std::cout.rdbuf(std::cerr.rdbuf());
