@@ -95,3 +95,34 @@ def test_edge_inputs(name):
     if n <= 5:
         a, r = P.astar(want_rows=False), R.astar(seqs)
         assert (a["g"], a["expansions"], a["generated"]) == (r["g"], r["expansions"], r["generated"])
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_seeded_fuzz(seed):
+    """Random small problems (N in 3..10, lengths 1..30, random or related sequences), random parents anywhere in the
+    lattice incl. its faces, a random hash / shift / partition count: weights, tables, h and every getNeigh record."""
+    import random
+    rng = random.Random(1000 + seed)
+    n = rng.choice([3, 4, 5, 6, 7, 8, 9, 10])
+    if rng.random() < 0.5:
+        seqs = ["".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(rng.randint(1, 30))) for _ in range(n)]
+    else:
+        seqs = family_seqs(n, rng.randint(2, 30), 2000 + seed, sub=rng.choice([0.05, 0.3]), indel=rng.choice([0.0, 0.1]))
+    d = R.dump(seqs)
+    assert np.array_equal(O.weights(seqs).view(np.uint32), d["weights"].view(np.uint32))
+    k = 0
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            assert np.array_equal(O.pair_table(seqs[i], seqs[j]), d["tables"][k])
+            k += 1
+    P = O.Problem(seqs)
+    fin = [len(s) for s in seqs]
+    pos = np.array([[rng.choice([0, f, rng.randint(0, f)]) for f in fin] for _ in range(5)], dtype=np.uint16)
+    g = np.array([rng.randint(0, 100000) for _ in range(5)], dtype=np.int32)
+    par = np.array([rng.randint(1, (1 << n) - 1) for _ in range(5)], dtype=np.int32)
+    vs, ht, sh = rng.choice([1, 2, 3, 4, 8, 16, 64]), rng.choice(["FZORDER", "PZORDER", "FSUM", "PSUM"]), rng.randint(0, 21)
+    ref = R.neigh(seqs, pos, g, par, vs, ht, sh)
+    for q in range(len(pos)):
+        mine = P.get_neigh(pos[q], g[q], par[q], vs, ht, sh)
+        assert int(g[q]) + P.calculate_h(pos[q]) == ref[q][0]
+        assert np.array_equal(mine, ref[q][1]), (seed, q, vs, ht, sh)
