@@ -120,3 +120,32 @@ def test_host_weights_refuses_residues_outside_the_cost_table():
         m.host_weights(["ACDZ", "ACDE", "ACD"])
     with pytest.raises(api.PastarError):
         m.host_weights(["ACDe", "ACDE", "ACD"])   # lowercase: also outside the 90 x 90 table
+
+
+def test_every_entry_point_refuses_null_arguments():
+    """No entry point dereferences a null context / buffer: PG_ERR_ARG (or 0 for the size getters), never a crash.  Run in a
+    child process so that a crash fails this test instead of ending the session; nothing here reaches the CUDA runtime."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import mpi_pastar_msa_b200 as m
+from mpi_pastar_msa_b200 import api
+L = C.CDLL(m.lib_path())
+z = C.c_void_p(0)
+getters = {"pg_search_outbox_capacity", "pg_search_region_bytes", "pg_xrec_stride", "pg_ctx_destroy", "pg_allow_extended_n"}
+skip = {"pg_release_cached_memory", "pg_default_cost_table", "pg_abi_version", "pg_last_error"}
+for name in sorted(api.EXPORTS):
+    if name in skip:
+        continue
+    f = getattr(L, name)
+    f.restype = C.c_int64 if name in ("pg_search_outbox_capacity", "pg_search_region_bytes") else C.c_int
+    r = f(z, z, z, z, z, z, z, z, z, z)
+    assert r == (0 if name in getters else 1), (name, r)
+L.pg_last_error.restype = C.c_char_p
+assert isinstance(L.pg_last_error(z), bytes)
+print("ok")
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0 and r.stdout.decode().strip() == "ok", (r.returncode, r.stderr.decode()[-1500:])
