@@ -149,3 +149,12 @@ print("ok")
 ''' % ROOT
     r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert r.returncode == 0 and r.stdout.decode().strip() == "ok", (r.returncode, r.stderr.decode()[-1500:])
+
+
+def test_ctx_create_validates_the_problem_before_touching_the_device():
+    """N outside {3..10, 14, 16} (msa_pastar_main.cpp:34-36; 11, 12, 13, 15 need pg_allow_extended_n) and empty sequences are
+    PG_ERR_ARG on any box - also where there is no device, i.e. the check does not depend on CUDA."""
+    for seqs in (["AC", "AD"], ["AC"] * 17, ["AC"] * 11, ["AC", "AD", ""]):
+        with pytest.raises(api.PastarError) as e:
+            m.PastarGPU(seqs, weights=None)
+        assert "PG_ERR_ARG" in str(e.value)
